@@ -1,0 +1,118 @@
+// Internal declarations shared by the libcalz translation units (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/calz.h"
+
+namespace calz {
+
+// ---------------------------------------------------------------------------------------------------
+// minimal NCCL surface, resolved with dlopen so that the library neither links against nor requires NCCL
+// on single-GPU hosts (the MEX use case) and shares torch's copy when loaded into a torch process.
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclFloat64 = 8 };   // ncclDataType_t: int8 0,uint8 1,int32 2,uint32 3,int64 4,uint64 5,f16 6,f32 7,f64 8
+enum { ncclSum = 0 };
+
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+int nccl_load(const char* path, NcclApi** api, std::string* err);
+
+// ---------------------------------------------------------------------------------------------------
+struct DevBuf {                      // grow-only device scratch
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace calz
+
+struct calz_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int64_t launches = 0;
+
+    // communicator
+    calz::NcclApi* nccl = nullptr;
+    calz::ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+
+    // options
+    int64_t opt_l2_chunk_bytes = 0;
+    int64_t opt_sell_sigma = 0;      // 0: choose
+    int64_t opt_csr_lanes = 0;       // 0: choose
+    int64_t opt_grid_mult = 8;       // CTAs per SM for the persistent tall-skinny kernels
+
+    // scratch
+    calz::DevBuf partials;           // per-CTA partial Gram/coefficient tiles
+    calz::DevBuf small;              // small device matrices (C, G, R, flags)
+    calz::DevBuf work[4];            // n x c work blocks (Y, Z, host-flavour staging ...)
+    calz::DevBuf tsqr_r;             // TSQR leaf R factors / tree
+    unsigned int* ticket = nullptr;  // "last CTA" tickets
+    double* pinned = nullptr;        // pinned host staging for small results
+    size_t pinned_bytes = 0;
+};
+
+namespace calz {
+
+extern std::string g_last_error;
+
+int set_error(calz_ctx* ctx, int code, const char* fmt, ...);
+int reserve(calz_ctx* ctx, DevBuf& b, size_t bytes);
+
+#define CALZ_CUDA(ctx, expr)                                                                        \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return calz::set_error((ctx), CALZ_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #expr, \
+                                   cudaGetErrorString(_e));                                         \
+    } while (0)
+
+#define CALZ_TRY(expr)                 \
+    do {                               \
+        int _s = (expr);               \
+        if (_s != CALZ_OK) return _s;  \
+    } while (0)
+
+#define CALZ_NCCL(ctx, expr)                                                                          \
+    do {                                                                                              \
+        int _e = (expr);                                                                              \
+        if (_e != calz::ncclSuccess)                                                                  \
+            return calz::set_error((ctx), CALZ_ERR_NCCL, "%s:%d %s: %s", __FILE__, __LINE__, #expr,   \
+                                   (ctx)->nccl->GetErrorString(_e));                                  \
+    } while (0)
+
+#define CALZ_LAUNCH_CHECK(ctx)          \
+    do {                                \
+        (ctx)->launches++;              \
+        CALZ_CUDA((ctx), cudaGetLastError()); \
+    } while (0)
+
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+
+// in-place sum over ranks of a small device fp64 buffer (no-op without a communicator)
+int allreduce_sum(calz_ctx* ctx, double* dev, size_t count);
+
+// host small algebra (smallalg.cu)
+void svd_singular_values(int c, const double* R, int ldR, double* sigma);   // one-sided Jacobi
+int  numerical_rank(int c, const double* R, int ldR, double tol);            // normalize.m:15-24
+
+}  // namespace calz

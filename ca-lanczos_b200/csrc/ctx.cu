@@ -1,0 +1,273 @@
+// Context, error handling, scratch management, NCCL plumbing and host small algebra of libcalz.
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "calz_internal.h"
+
+namespace calz {
+
+std::string g_last_error;
+
+int set_error(calz_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+int reserve(calz_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (b.bytes >= bytes && b.p) return CALZ_OK;
+    if (b.p) {
+        // the old block may still be in use by kernels queued on the stream
+        CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        CALZ_CUDA(ctx, cudaFree(b.p));
+        b.p = nullptr;
+        b.bytes = 0;
+    }
+    size_t want = (bytes + 255) & ~size_t(255);
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return set_error(ctx, CALZ_ERR_ALLOC, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    b.bytes = want;
+    return CALZ_OK;
+}
+
+// --------------------------------------------------------------------------------------------- NCCL
+static NcclApi g_nccl;
+
+int nccl_load(const char* path, NcclApi** api, std::string* err) {
+    if (g_nccl.handle) {
+        *api = &g_nccl;
+        return CALZ_OK;
+    }
+    void* h = nullptr;
+    if (path && path[0]) h = dlopen(path, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);   // torch's copy, if resident
+    if (!h) {
+        const char* env = getenv("CALZ_NCCL_LIB");
+        if (env && env[0]) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    }
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) {
+        *err = std::string("cannot load libnccl.so.2: ") + dlerror();
+        return CALZ_ERR_NCCL;
+    }
+    NcclApi a;
+    a.handle = h;
+#define CALZ_SYM(field, name)                                    \
+    *(void**)(&a.field) = dlsym(h, name);                        \
+    if (!a.field) {                                              \
+        *err = std::string("libnccl: missing symbol ") + name;   \
+        return CALZ_ERR_NCCL;                                    \
+    }
+    CALZ_SYM(GetUniqueId, "ncclGetUniqueId")
+    CALZ_SYM(CommInitRank, "ncclCommInitRank")
+    CALZ_SYM(CommDestroy, "ncclCommDestroy")
+    CALZ_SYM(AllReduce, "ncclAllReduce")
+    CALZ_SYM(Send, "ncclSend")
+    CALZ_SYM(Recv, "ncclRecv")
+    CALZ_SYM(GroupStart, "ncclGroupStart")
+    CALZ_SYM(GroupEnd, "ncclGroupEnd")
+    CALZ_SYM(GetErrorString, "ncclGetErrorString")
+#undef CALZ_SYM
+    g_nccl = a;
+    *api = &g_nccl;
+    return CALZ_OK;
+}
+
+int allreduce_sum(calz_ctx* ctx, double* dev, size_t count) {
+    if (ctx->nranks <= 1 || count == 0) return CALZ_OK;
+    CALZ_NCCL(ctx, ctx->nccl->AllReduce(dev, dev, count, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
+    return CALZ_OK;
+}
+
+// --------------------------------------------------------------------------------------------- small algebra
+// Singular values of a small c x c matrix by one-sided (Hestenes) Jacobi; replaces svd(R) in normalize.m:15.
+void svd_singular_values(int c, const double* R, int ldR, double* sigma) {
+    std::vector<double> U((size_t)c * c);
+    for (int j = 0; j < c; ++j)
+        for (int i = 0; i < c; ++i) U[(size_t)j * c + i] = R[(size_t)j * ldR + i];
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < c - 1; ++p)
+            for (int q = p + 1; q < c; ++q) {
+                double a = 0, b = 0, g = 0;
+                for (int i = 0; i < c; ++i) {
+                    double up = U[(size_t)p * c + i], uq = U[(size_t)q * c + i];
+                    a += up * up; b += uq * uq; g += up * uq;
+                }
+                if (g == 0.0) continue;
+                double denom = sqrt(a * b);
+                if (denom > 0 && fabs(g) <= 1e-17 * denom) continue;
+                off = std::max(off, denom > 0 ? fabs(g) / denom : 0.0);
+                double zeta = (b - a) / (2.0 * g);
+                double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+                double cs = 1.0 / sqrt(1.0 + t * t), sn = cs * t;
+                for (int i = 0; i < c; ++i) {
+                    double up = U[(size_t)p * c + i], uq = U[(size_t)q * c + i];
+                    U[(size_t)p * c + i] = cs * up - sn * uq;
+                    U[(size_t)q * c + i] = sn * up + cs * uq;
+                }
+            }
+        if (off < 1e-15) break;
+    }
+    for (int j = 0; j < c; ++j) {
+        double a = 0;
+        for (int i = 0; i < c; ++i) a += U[(size_t)j * c + i] * U[(size_t)j * c + i];
+        sigma[j] = sqrt(a);
+    }
+    std::sort(sigma, sigma + c, [](double x, double y) { return x > y; });
+}
+
+// normalize.m:15-24: rank = index of the first sigma_i <= tol*sigma_1, minus one; ncols if none.
+int numerical_rank(int c, const double* R, int ldR, double tol) {
+    std::vector<double> s(c);
+    svd_singular_values(c, R, ldR, s.data());
+    double abs_tol = tol * s[0];
+    for (int i = 0; i < c; ++i)
+        if (!(s[i] > abs_tol)) return i;
+    return c;
+}
+
+}  // namespace calz
+
+using namespace calz;
+
+// --------------------------------------------------------------------------------------------- C ABI
+extern "C" {
+
+int calz_version(void) { return 100; }
+
+const char* calz_last_error(const calz_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int calz_init(int device, calz_ctx** out) {
+    if (!out) return set_error(nullptr, CALZ_ERR_BADARG, "calz_init: ctx is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return set_error(nullptr, CALZ_ERR_CUDA, "calz_init: no CUDA device (%s); there is no CPU fallback",
+                         e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= ndev) return set_error(nullptr, CALZ_ERR_BADARG, "calz_init: bad device %d", device);
+    calz_ctx* ctx = new calz_ctx();
+    ctx->device = device;
+    CALZ_CUDA(ctx, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CALZ_CUDA(ctx, cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        delete ctx;
+        return set_error(nullptr, CALZ_ERR_CUDA, "calz_init: device sm_%d%d is not a Blackwell B200 (sm_100a) part",
+                         prop.major, prop.minor);
+    }
+    ctx->num_sms = prop.multiProcessorCount;
+    CALZ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+    CALZ_CUDA(ctx, cudaMalloc(&ctx->ticket, 64 * sizeof(unsigned int)));
+    CALZ_CUDA(ctx, cudaMemset(ctx->ticket, 0, 64 * sizeof(unsigned int)));
+    ctx->pinned_bytes = 1 << 20;
+    CALZ_CUDA(ctx, cudaMallocHost(&ctx->pinned, ctx->pinned_bytes));
+    *out = ctx;
+    return CALZ_OK;
+}
+
+int calz_finalize(calz_ctx* ctx) {
+    if (!ctx) return CALZ_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
+    DevBuf* bufs[] = {&ctx->partials, &ctx->small, &ctx->work[0], &ctx->work[1], &ctx->work[2], &ctx->work[3], &ctx->tsqr_r};
+    for (DevBuf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (ctx->ticket) cudaFree(ctx->ticket);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return CALZ_OK;
+}
+
+int calz_set_stream(calz_ctx* ctx, void* s) {
+    if (!ctx) return CALZ_ERR_BADARG;
+    CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (s) {
+        ctx->stream = (cudaStream_t)s;
+        ctx->own_stream = false;
+    } else {
+        CALZ_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return CALZ_OK;
+}
+
+void* calz_get_stream(calz_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int calz_sync(calz_ctx* ctx) {
+    if (!ctx) return CALZ_ERR_BADARG;
+    CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CALZ_OK;
+}
+
+int64_t calz_launch_count(calz_ctx* ctx, int reset) {
+    if (!ctx) return 0;
+    int64_t v = ctx->launches;
+    if (reset) ctx->launches = 0;
+    return v;
+}
+
+int calz_set_option(calz_ctx* ctx, const char* key, int64_t value) {
+    if (!ctx || !key) return CALZ_ERR_BADARG;
+    if (!strcmp(key, "mpk_l2_chunk_bytes")) ctx->opt_l2_chunk_bytes = value;
+    else if (!strcmp(key, "sell_sigma")) ctx->opt_sell_sigma = value;
+    else if (!strcmp(key, "csr_lanes")) ctx->opt_csr_lanes = value;
+    else if (!strcmp(key, "grid_mult")) ctx->opt_grid_mult = value > 0 ? value : 1;
+    else return set_error(ctx, CALZ_ERR_BADARG, "calz_set_option: unknown key '%s'", key);
+    return CALZ_OK;
+}
+
+int calz_comm_unique_id(char id_out[128], const char* nccl_lib) {
+    NcclApi* api = nullptr;
+    std::string err;
+    if (nccl_load(nccl_lib, &api, &err) != CALZ_OK) return set_error(nullptr, CALZ_ERR_NCCL, "%s", err.c_str());
+    ncclUniqueId id;
+    int e = api->GetUniqueId(&id);
+    if (e != ncclSuccess) return set_error(nullptr, CALZ_ERR_NCCL, "ncclGetUniqueId: %s", api->GetErrorString(e));
+    memcpy(id_out, id.internal, 128);
+    return CALZ_OK;
+}
+
+int calz_comm_init(calz_ctx* ctx, int nranks, int rank, const char id[128], const char* nccl_lib) {
+    if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return set_error(ctx, CALZ_ERR_BADARG, "calz_comm_init: bad arguments");
+    if (nranks == 1) {
+        ctx->rank = 0;
+        ctx->nranks = 1;
+        return CALZ_OK;
+    }
+    std::string err;
+    if (nccl_load(nccl_lib, &ctx->nccl, &err) != CALZ_OK) return set_error(ctx, CALZ_ERR_NCCL, "%s", err.c_str());
+    CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    ncclUniqueId uid;
+    memcpy(uid.internal, id, 128);
+    CALZ_NCCL(ctx, ctx->nccl->CommInitRank(&ctx->comm, nranks, uid, rank));
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    return CALZ_OK;
+}
+
+int calz_comm_rank(const calz_ctx* ctx, int* rank, int* nranks) {
+    if (!ctx) return CALZ_ERR_BADARG;
+    if (rank) *rank = ctx->rank;
+    if (nranks) *nranks = ctx->nranks;
+    return CALZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,42 @@
+// Device sparse matrix of one rank: owned rows + level-s ghost closure, CSR and/or SELL-32-sigma.
+#pragma once
+#include "calz_internal.h"
+
+struct calz_mat {
+    calz_ctx* ctx = nullptr;
+    int64_t n_glob = 0, row_lo = 0, row_hi = 0;      // owned global rows [row_lo,row_hi)
+    int64_t n_own = 0, n_loc = 0, own_off = 0;       // local index space: ascending global index over R_s
+    int64_t nnz_loc = 0, bandwidth = 0;
+    int s_max = 0;
+    int layout = CALZ_LAYOUT_CSR;
+
+    std::vector<int64_t> ghost_glob;                 // sorted global indices of ghost_s(p)
+    std::vector<int64_t> hull_lo, hull_hi;           // hull of local rows with level <= L, L = 0..s_max
+
+    // exchange plan (per peer)
+    std::vector<int64_t> recv_off, recv_cnt;         // ghosts from peer q: contiguous run of local indices
+    std::vector<std::vector<int64_t>> recv_glob;     // ... and their global indices (bit-exact object)
+    std::vector<std::vector<int64_t>> send_glob;     // what peer q wants from me (global indices, sorted)
+    std::vector<int64_t> send_off, send_cnt;         // offsets into d_send_idx / d_send_buf
+    std::vector<char> send_contig;                   // send list is a contiguous local range: no pack
+    int32_t* d_send_idx = nullptr;                   // local indices to pack, all peers concatenated
+    double* d_send_buf = nullptr;
+
+    // CSR (local indices)
+    int32_t* d_rowptr = nullptr;
+    int32_t* d_colind = nullptr;
+    double* d_val = nullptr;
+    int csr_lanes = 8;
+
+    // SELL-32-sigma (column-major inside a slice of 32 rows)
+    int64_t sell_slices = 0, sell_padded = 0;
+    int sell_sigma = 32;
+    int32_t* d_slice_ptr = nullptr;                  // entry offset of slice / 32 (i.e. first "row" of width)
+    int32_t* d_sell_col = nullptr;
+    double* d_sell_val = nullptr;
+    int32_t* d_perm = nullptr;                       // sorted position -> local row (NULL: identity)
+
+    // basis workspace n_loc x (s_max+1), ghosts included
+    double* d_W = nullptr;
+    int64_t ldW = 0;
+};

@@ -1,0 +1,298 @@
+// K1: the s-step matrix powers kernel (fp64).  One halo exchange, then s SpMV steps back to back with the
+// Newton shift (and the conjugate-pair term) fused into the SpMV epilogue.
+//
+// Reference counterparts: SpMV.m:6-8, matrix_powers_monomial.m:6-12, matrix_powers_newton.m:15-54.
+// Arithmetic order follows the reference: the full row sum first (ascending column order), then
+// ``w - re(l_k)*x_i`` as a rounded product and a rounded subtraction, then ``+ im(l_k)^2*xprev_i``.
+#include <algorithm>
+
+#include "matrix.h"
+
+using namespace calz;
+
+namespace {
+
+constexpr int kSpmvThreads = 256;
+
+__device__ __forceinline__ double newton_epilogue(double w, double xi, double xp, double shift, double pair) {
+    // matrix_powers_newton.m:34,40-41,43 -- two (three) separately rounded operations, no contraction
+    double r = __dsub_rn(w, __dmul_rn(shift, xi));
+    if (pair != 0.0) r = __dadd_rn(r, __dmul_rn(pair, xp));
+    return r;
+}
+
+// ---- SELL-32-sigma: one warp per slice, one lane per row, column-major slice => fully coalesced A stream
+template <bool NEWTON>
+__global__ void __launch_bounds__(kSpmvThreads)
+k_spmv_sell(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ col, const double* __restrict__ val,
+            const int32_t* __restrict__ perm, const double* __restrict__ x, const double* __restrict__ xprev,
+            double* __restrict__ y, int64_t slice_lo, int64_t slice_hi, int64_t n_loc, double shift, double pair) {
+    const int lane = threadIdx.x & 31;
+    const int64_t slice = slice_lo + (int64_t)blockIdx.x * (kSpmvThreads / 32) + (threadIdx.x >> 5);
+    if (slice >= slice_hi) return;
+    const int32_t p0 = __ldg(slice_ptr + slice), p1 = __ldg(slice_ptr + slice + 1);
+    const int64_t base = (int64_t)p0 * 32 + lane;
+    const double* __restrict__ v = val + base;
+    const int32_t* __restrict__ c = col + base;
+    const int w = p1 - p0;
+    double sum = 0.0;
+    int j = 0;
+    for (; j + 4 <= w; j += 4) {
+        const double a0 = __ldg(v + (j + 0) * 32), a1 = __ldg(v + (j + 1) * 32);
+        const double a2 = __ldg(v + (j + 2) * 32), a3 = __ldg(v + (j + 3) * 32);
+        const int32_t c0 = __ldg(c + (j + 0) * 32), c1 = __ldg(c + (j + 1) * 32);
+        const int32_t c2 = __ldg(c + (j + 2) * 32), c3 = __ldg(c + (j + 3) * 32);
+        const double x0 = x[c0], x1 = x[c1], x2 = x[c2], x3 = x[c3];
+        sum = fma(a0, x0, sum);
+        sum = fma(a1, x1, sum);
+        sum = fma(a2, x2, sum);
+        sum = fma(a3, x3, sum);
+    }
+    for (; j < w; ++j) sum = fma(__ldg(v + j * 32), x[__ldg(c + j * 32)], sum);
+    const int64_t r = slice * 32 + lane;
+    if (r < n_loc) {
+        const int64_t row = perm ? (int64_t)__ldg(perm + r) : r;
+        if (NEWTON) sum = newton_epilogue(sum, x[row], pair != 0.0 ? xprev[row] : 0.0, shift, pair);
+        y[row] = sum;
+    }
+}
+
+// ---- CSR: L lanes per row (L chosen from the mean row length), shuffle reduction
+template <int L, bool NEWTON>
+__global__ void __launch_bounds__(kSpmvThreads)
+k_spmv_csr(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, const double* __restrict__ val,
+           const double* __restrict__ x, const double* __restrict__ xprev, double* __restrict__ y,
+           int64_t row_lo, int64_t row_hi, double shift, double pair) {
+    const int64_t gid = (int64_t)blockIdx.x * kSpmvThreads + threadIdx.x;
+    const int64_t row = row_lo + gid / L;
+    const int sub = (int)(gid % L);
+    double sum = 0.0;
+    if (row < row_hi) {
+        const int32_t e0 = __ldg(rowptr + row), e1 = __ldg(rowptr + row + 1);
+        for (int32_t e = e0 + sub; e < e1; e += L) sum = fma(__ldg(val + e), x[__ldg(col + e)], sum);
+    }
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (row < row_hi && sub == 0) {
+        if (NEWTON) sum = newton_epilogue(sum, x[row], pair != 0.0 ? xprev[row] : 0.0, shift, pair);
+        y[row] = sum;
+    }
+}
+
+__global__ void k_pack(const double* __restrict__ x, const int32_t* __restrict__ idx, double* __restrict__ buf, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) buf[i] = x[idx[i]];
+}
+
+template <bool NEWTON>
+int launch_csr(calz_mat* m, const double* x, const double* xp, double* y, int64_t lo, int64_t hi, double shift, double pair) {
+    calz_ctx* ctx = m->ctx;
+    const int L = m->csr_lanes;
+    const int64_t threads = (hi - lo) * L;
+    const unsigned grid = (unsigned)((threads + kSpmvThreads - 1) / kSpmvThreads);
+#define CALZ_CSR_CASE(LL)                                                                                     \
+    case LL:                                                                                                  \
+        k_spmv_csr<LL, NEWTON><<<grid, kSpmvThreads, 0, ctx->stream>>>(m->d_rowptr, m->d_colind, m->d_val, x, \
+                                                                       xp, y, lo, hi, shift, pair);           \
+        break;
+    switch (L) {
+        CALZ_CSR_CASE(1) CALZ_CSR_CASE(2) CALZ_CSR_CASE(4) CALZ_CSR_CASE(8) CALZ_CSR_CASE(16) CALZ_CSR_CASE(32)
+        default: return set_error(ctx, CALZ_ERR_BADARG, "csr_lanes must be a power of two <= 32");
+    }
+#undef CALZ_CSR_CASE
+    CALZ_LAUNCH_CHECK(ctx);
+    return CALZ_OK;
+}
+
+// one SpMV step on local rows [lo,hi) (already aligned to the layout granule)
+int spmv_step(calz_mat* m, const double* x, const double* xp, double* y, int64_t lo, int64_t hi, bool newton,
+              double shift, double pair) {
+    if (hi <= lo) return CALZ_OK;
+    calz_ctx* ctx = m->ctx;
+    if (m->layout == CALZ_LAYOUT_SELL) {
+        const int64_t s0 = lo / 32, s1 = (hi + 31) / 32;
+        const unsigned grid = (unsigned)((s1 - s0 + kSpmvThreads / 32 - 1) / (kSpmvThreads / 32));
+        if (newton)
+            k_spmv_sell<true><<<grid, kSpmvThreads, 0, ctx->stream>>>(m->d_slice_ptr, m->d_sell_col, m->d_sell_val, m->d_perm,
+                                                                      x, xp, y, s0, s1, m->n_loc, shift, pair);
+        else
+            k_spmv_sell<false><<<grid, kSpmvThreads, 0, ctx->stream>>>(m->d_slice_ptr, m->d_sell_col, m->d_sell_val, m->d_perm,
+                                                                       x, xp, y, s0, s1, m->n_loc, 0.0, 0.0);
+        CALZ_LAUNCH_CHECK(ctx);
+        return CALZ_OK;
+    }
+    return newton ? launch_csr<true>(m, x, xp, y, lo, hi, shift, pair) : launch_csr<false>(m, x, xp, y, lo, hi, 0.0, 0.0);
+}
+
+// the ONE level-s halo exchange of an outer step: column `col` of the workspace
+int halo_exchange(calz_mat* m, double* w) {
+    calz_ctx* ctx = m->ctx;
+    const int P = ctx->nranks;
+    if (P <= 1) return CALZ_OK;
+    for (int q = 0; q < P; ++q)
+        if (m->send_cnt[q] && !m->send_contig[q]) {
+            const int64_t n = m->send_cnt[q];
+            k_pack<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(w, m->d_send_idx + m->send_off[q],
+                                                                        m->d_send_buf + m->send_off[q], n);
+            CALZ_LAUNCH_CHECK(ctx);
+        }
+    CALZ_NCCL(ctx, ctx->nccl->GroupStart());
+    for (int q = 0; q < P; ++q) {
+        if (m->send_cnt[q]) {
+            const double* src = m->send_contig[q] ? w + (m->own_off + (m->send_glob[q][0] - m->row_lo))
+                                                  : m->d_send_buf + m->send_off[q];
+            CALZ_NCCL(ctx, ctx->nccl->Send(src, (size_t)m->send_cnt[q], ncclFloat64, q, ctx->comm, ctx->stream));
+        }
+        if (m->recv_cnt[q])
+            CALZ_NCCL(ctx, ctx->nccl->Recv(w + m->recv_off[q], (size_t)m->recv_cnt[q], ncclFloat64, q, ctx->comm, ctx->stream));
+    }
+    CALZ_NCCL(ctx, ctx->nccl->GroupEnd());
+    return CALZ_OK;
+}
+
+struct Shifts {
+    std::vector<double> re, pair;   // per step: real shift, im^2 factor (0 if none)
+    bool newton = false;
+};
+
+int make_shifts(calz_ctx* ctx, int s, const double* re, const double* im, int modifiedp, int monomial, Shifts& out) {
+    out.re.assign(s, 0.0);
+    out.pair.assign(s, 0.0);
+    out.newton = !monomial;
+    if (monomial) return CALZ_OK;
+    if (!re) return set_error(ctx, CALZ_ERR_BADARG, "mpk_newton: shift_re is NULL");
+    for (int k = 0; k < s; ++k) {
+        const double i = im ? im[k] : 0.0;
+        out.re[k] = re[k];
+        if (i != 0.0) {
+            if (!modifiedp)
+                return set_error(ctx, CALZ_ERR_UNSUPPORTED,
+                                 "matrix_powers_newton with modifiedp=0 and a complex shift needs complex vectors");
+            if (i < 0.0) {
+                if (k == 0) return set_error(ctx, CALZ_ERR_SHIFT, "k==1, but shift %e has a negative imaginary part", re[k]);
+                out.pair[k] = i * i;     // matrix_powers_newton.m:40-41
+            }
+        }
+    }
+    return CALZ_OK;
+}
+
+int mpk_run(calz_mat* m, const double* v, int s, const Shifts& sh) {
+    calz_ctx* ctx = m->ctx;
+    if (s < 1 || s > m->s_max) return set_error(ctx, CALZ_ERR_BADARG, "mpk: s=%d outside [1,%d] (s_max of the matrix)", s, m->s_max);
+    CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    double* W = m->d_W;
+    const int64_t ld = m->ldW;
+    if (v != W + m->own_off)
+        CALZ_CUDA(ctx, cudaMemcpyAsync(W + m->own_off, v, (size_t)m->n_own * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    CALZ_TRY(halo_exchange(m, W));
+
+    const int64_t gran = (m->layout == CALZ_LAYOUT_SELL) ? (m->d_perm ? m->sell_sigma : 32) : 1;
+    auto lo_of = [&](int k) { return (m->hull_lo[s - k] / gran) * gran; };
+    auto hi_of = [&](int k) { return std::min<int64_t>(m->n_loc, round_up(m->hull_hi[s - k], gran)); };
+    auto step = [&](int k, int64_t lo, int64_t hi) -> int {
+        lo = std::max(lo, lo_of(k));
+        hi = std::min(hi, hi_of(k));
+        const double* x = W + (int64_t)(k - 1) * ld;
+        const double* xp = (k >= 2) ? W + (int64_t)(k - 2) * ld : x;
+        return spmv_step(m, x, xp, W + (int64_t)k * ld, lo, hi, sh.newton, sh.re[k - 1], sh.pair[k - 1]);
+    };
+
+    // Temporal blocking through the 126 MB L2: process the rows in chunks whose slice of A stays resident,
+    // skewing step k by (k-1) bandwidths so that every dependency is already computed.
+    const int64_t bytes_per_row = m->n_loc ? (12 * m->nnz_loc) / m->n_loc + 24 : 0;
+    const int64_t bwid = round_up(std::max<int64_t>(m->bandwidth, 1), gran);
+    int64_t chunk_rows = 0;
+    if (ctx->opt_l2_chunk_bytes > 0 && bytes_per_row > 0) {
+        chunk_rows = round_up(std::max<int64_t>(ctx->opt_l2_chunk_bytes / bytes_per_row, gran), gran);
+        if (chunk_rows < 2 * bwid || chunk_rows >= m->n_loc) chunk_rows = 0;   // band too wide / matrix fits: plain sweeps
+    }
+    if (chunk_rows == 0) {
+        for (int k = 1; k <= s; ++k) CALZ_TRY(step(k, 0, m->n_loc));
+    } else {
+        const int64_t span = m->n_loc + (int64_t)(s - 1) * bwid;
+        for (int64_t c0 = 0; c0 < span; c0 += chunk_rows)
+            for (int k = 1; k <= s; ++k) {
+                const int64_t lo = c0 - (int64_t)(k - 1) * bwid, hi = lo + chunk_rows;
+                if (hi <= 0 || lo >= m->n_loc) continue;
+                CALZ_TRY(step(k, std::max<int64_t>(lo, 0), std::min<int64_t>(hi, m->n_loc)));
+            }
+    }
+    return CALZ_OK;
+}
+
+int copy_out(calz_mat* m, int col0, int ncols, double* V, int64_t ldV) {
+    calz_ctx* ctx = m->ctx;
+    const double* src = m->d_W + m->own_off + (int64_t)col0 * m->ldW;
+    if (V == src && ldV == m->ldW) return CALZ_OK;
+    if (ldV < m->n_own) return set_error(ctx, CALZ_ERR_BADARG, "ldV < n_own");
+    CALZ_CUDA(ctx, cudaMemcpy2DAsync(V, (size_t)ldV * sizeof(double), src, (size_t)m->ldW * sizeof(double),
+                                     (size_t)m->n_own * sizeof(double), (size_t)ncols, cudaMemcpyDeviceToDevice, ctx->stream));
+    return CALZ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int calz_mpk_inplace(calz_mat* m, const double* v, int s, const double* shift_re, const double* shift_im,
+                     int modifiedp, int monomial, double** V, int64_t* ldV) {
+    if (!m || !v) return set_error(m ? m->ctx : nullptr, CALZ_ERR_BADARG, "calz_mpk_inplace: bad arguments");
+    Shifts sh;
+    CALZ_TRY(make_shifts(m->ctx, s, shift_re, shift_im, modifiedp, monomial, sh));
+    CALZ_TRY(mpk_run(m, v, s, sh));
+    if (V) *V = m->d_W + m->own_off;
+    if (ldV) *ldV = m->ldW;
+    return CALZ_OK;
+}
+
+int calz_mpk_newton(calz_mat* m, const double* v, int s, const double* shift_re, const double* shift_im,
+                    int modifiedp, double* V, int64_t ldV) {
+    if (!m || !v || !V) return set_error(m ? m->ctx : nullptr, CALZ_ERR_BADARG, "calz_mpk_newton: bad arguments");
+    CALZ_TRY(calz_mpk_inplace(m, v, s, shift_re, shift_im, modifiedp, 0, nullptr, nullptr));
+    return copy_out(m, 0, s + 1, V, ldV);
+}
+
+int calz_mpk_monomial(calz_mat* m, const double* q, int s, double* V, int64_t ldV) {
+    if (!m || !q || !V) return set_error(m ? m->ctx : nullptr, CALZ_ERR_BADARG, "calz_mpk_monomial: bad arguments");
+    CALZ_TRY(calz_mpk_inplace(m, q, s, nullptr, nullptr, 0, 1, nullptr, nullptr));
+    return copy_out(m, 1, s, V, ldV);       // matrix_powers_monomial.m:7 -- q itself is not returned
+}
+
+int calz_spmv(calz_mat* m, const double* x, double* y) {
+    if (!m || !x || !y) return set_error(m ? m->ctx : nullptr, CALZ_ERR_BADARG, "calz_spmv: bad arguments");
+    CALZ_TRY(calz_mpk_inplace(m, x, 1, nullptr, nullptr, 0, 1, nullptr, nullptr));
+    return copy_out(m, 1, 1, y, m->n_own);
+}
+
+// ---- host-pointer flavours (what the MEX gateways call): H2D of the vector, D2H of the basis
+static int mpk_host(calz_mat* m, const double* v, int s, const double* re, const double* im, int modifiedp,
+                    int monomial, int col0, int ncols, double* V, int64_t ldV) {
+    if (!m || !v || !V) return set_error(m ? m->ctx : nullptr, CALZ_ERR_BADARG, "mpk_host: bad arguments");
+    calz_ctx* ctx = m->ctx;
+    if (ldV < m->n_own) return set_error(ctx, CALZ_ERR_BADARG, "ldV < n");
+    CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    double* w0 = m->d_W + m->own_off;
+    CALZ_CUDA(ctx, cudaMemcpyAsync(w0, v, (size_t)m->n_own * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CALZ_TRY(calz_mpk_inplace(m, w0, s, re, im, modifiedp, monomial, nullptr, nullptr));
+    CALZ_CUDA(ctx, cudaMemcpy2DAsync(V, (size_t)ldV * sizeof(double), w0 + (int64_t)col0 * m->ldW,
+                                     (size_t)m->ldW * sizeof(double), (size_t)m->n_own * sizeof(double), (size_t)ncols,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+    CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CALZ_OK;
+}
+
+int calz_spmv_host(calz_mat* m, const double* x, double* y) {
+    return mpk_host(m, x, 1, nullptr, nullptr, 0, 1, 1, 1, y, m ? m->n_own : 0);
+}
+
+int calz_mpk_monomial_host(calz_mat* m, const double* q, int s, double* V, int64_t ldV) {
+    return mpk_host(m, q, s, nullptr, nullptr, 0, 1, 1, s, V, ldV);
+}
+
+int calz_mpk_newton_host(calz_mat* m, const double* v, int s, const double* shift_re, const double* shift_im,
+                         int modifiedp, double* V, int64_t ldV) {
+    return mpk_host(m, v, s, shift_re, shift_im, modifiedp, 0, 0, s + 1, V, ldV);
+}
+
+}  // extern "C"

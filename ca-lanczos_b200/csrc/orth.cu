@@ -1,0 +1,369 @@
+// Block orthogonalisation entry points: tsqr / cholqr / normalize / project / projectAndNormalize.
+//
+// The control flow of projectAndNormalize.m:3-90 is kept exactly -- norms before, project, normalize, the 50 %
+// norm-drop test, the second pass on the UN-normalised Y, the coefficient sum -- but it runs without a host
+// round trip: the test result is a device flag and the pass-2 kernels are predicated on it, so one call is
+// one uninterrupted kernel train (plus small all-reduces when row-partitioned) and a single D2H copy of
+// the small results at the end.  Work the reference computes and then discards when pass 2 fires (the Q of
+// the first QR, projectAndNormalize.m:26 vs :63-64) is simply not launched.
+#include <string.h>
+
+#include <algorithm>
+
+#include "tsops.cuh"
+
+using namespace calz;
+
+namespace {
+
+struct SmallLayout {            // device scratch for one projectAndNormalize call (doubles)
+    int* flags;                 // [0] second pass, [1] chol info pass 1, [2] chol info pass 2
+    std::vector<double*> C1, C2;
+    std::vector<int> ld1;
+    double *G, *R1, *R2;
+    size_t doubles;
+};
+
+int small_scratch(calz_ctx* ctx, size_t doubles, double** p) {
+    CALZ_TRY(reserve(ctx, ctx->small, doubles * sizeof(double)));
+    if (doubles * sizeof(double) > ctx->pinned_bytes) {
+        CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        ctx->pinned_bytes = doubles * sizeof(double) * 2;
+        CALZ_CUDA(ctx, cudaMallocHost(&ctx->pinned, ctx->pinned_bytes));
+    }
+    *p = (double*)ctx->small.p;
+    return CALZ_OK;
+}
+
+bool empty_block(const double* const* Qblk, const int* mcols, int i) { return !Qblk || !Qblk[i] || !mcols || mcols[i] <= 0; }
+
+// QR of S (n x c) by `backend`: R -> R_dev; with CholQR the Gram matrix goes through G_dev.
+// decision (optional): norm-drop flag from the columns of R against nb2.
+int factor_r(calz_ctx* ctx, int backend, int64_t n, int c, const double* S, int64_t ldS, double* G_dev, double* R_dev,
+             int* info_dev, const double* nb2, int nb2_stride, int* flag_dev, const int* pred, int want) {
+    if (backend == CALZ_QR_CHOLQR) {
+        CALZ_TRY(tsmm_tn(ctx, n, one_panel(S, ldS, c), S, ldS, c, G_dev, c, true, pred, want, true));
+        return chol_small(ctx, c, G_dev, R_dev, info_dev, nb2, nb2_stride, flag_dev, pred, want);
+    }
+    CALZ_TRY(tsqr_factor(ctx, n, c, S, ldS, R_dev, pred, want));
+    if (nb2) CALZ_TRY(norm_drop_decision(ctx, c, R_dev, nb2, nb2_stride, flag_dev));
+    return CALZ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int calz_gram(calz_ctx* ctx, int64_t n, int m, const double* A, int64_t ldA, int c, const double* B, int64_t ldB, double* C_dev) {
+    if (!ctx || !A || !B || !C_dev || n < 0 || m < 1 || c < 1) return set_error(ctx, CALZ_ERR_BADARG, "calz_gram: bad arguments");
+    CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    return tsmm_tn(ctx, n, one_panel(A, ldA, m), B, ldB, c, C_dev, m, A == B && ldA == ldB && m == c, nullptr, 0, true);
+}
+
+int calz_cholqr(calz_ctx* ctx, int64_t n, int c, const double* X, int64_t ldX, double* Q, int64_t ldQ, double* R, int* info) {
+    if (!ctx || !X || !Q || !R || n < 1 || c < 1 || c > kMaxC) return set_error(ctx, CALZ_ERR_BADARG, "calz_cholqr: bad arguments");
+    CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    double* sm;
+    CALZ_TRY(small_scratch(ctx, 2 + 2 * (size_t)c * c, &sm));
+    int* flags = (int*)sm;
+    double *G = sm + 2, *Rd = G + (size_t)c * c;
+    CALZ_TRY(factor_r(ctx, CALZ_QR_CHOLQR, n, c, X, ldX, G, Rd, flags, nullptr, 0, nullptr, nullptr, 0));
+    CALZ_TRY(ts_trsolve(ctx, n, c, X, ldX, Rd, Rd, nullptr, Q, ldQ));
+    CALZ_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, sm, (2 + 2 * (size_t)c * c) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int inf = ((int*)ctx->pinned)[0];
+    memcpy(R, ctx->pinned + 2 + (size_t)c * c, (size_t)c * c * sizeof(double));
+    if (info) *info = inf;
+    if (inf) return set_error(ctx, CALZ_ERR_CHOL, "cholqr: Gram matrix not positive definite at pivot %d", inf);
+    return CALZ_OK;
+}
+
+int calz_tsqr(calz_ctx* ctx, int64_t n, int c, const double* A, int64_t ldA, double* Q, int64_t ldQ, double* R) {
+    if (!ctx || !A || !Q || !R || n < 1 || c < 1 || c > kMaxC) return set_error(ctx, CALZ_ERR_BADARG, "calz_tsqr: bad arguments");
+    CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    double* sm;
+    CALZ_TRY(small_scratch(ctx, (size_t)c * c, &sm));
+    CALZ_TRY(tsqr_factor(ctx, n, c, A, ldA, sm, nullptr, 0));
+    CALZ_TRY(tsqr_form_q(ctx, n, c, A, ldA, Q, ldQ));
+    CALZ_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, sm, (size_t)c * c * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    memcpy(R, ctx->pinned, (size_t)c * c * sizeof(double));
+    return CALZ_OK;
+}
+
+int calz_normalize(calz_ctx* ctx, int64_t n, int c, const double* X, int64_t ldX, int backend, double tol, double* Q,
+                   int64_t ldQ, double* R, int* rank) {
+    if (tol <= 0) tol = 1.0e-8;      // normalize.m:8-10
+    int st;
+    if (backend == CALZ_QR_CHOLQR) {
+        int info = 0;
+        st = calz_cholqr(ctx, n, c, X, ldX, Q, ldQ, R, &info);
+    } else if (backend == CALZ_QR_TSQR) {
+        st = calz_tsqr(ctx, n, c, X, ldX, Q, ldQ, R);
+    } else {
+        return set_error(ctx, CALZ_ERR_BADARG, "calz_normalize: unknown backend %d", backend);
+    }
+    CALZ_TRY(st);
+    if (rank) *rank = numerical_rank(c, R, c, tol);
+    return CALZ_OK;
+}
+
+int calz_project(calz_ctx* ctx, int64_t n, int nblk, const double* const* Qblk, const int64_t* ldQ, const int* mcols,
+                 int c, double* X, int64_t ldX, int doreorth, double* const* Rblk) {
+    if (!ctx || !X || n < 1 || c < 1 || c > kMaxC || nblk < 0) return set_error(ctx, CALZ_ERR_BADARG, "calz_project: bad arguments");
+    CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t tot = 0;
+    for (int i = 0; i < nblk; ++i)
+        if (!empty_block(Qblk, mcols, i)) tot += (size_t)mcols[i] * c;
+    double* sm;
+    const size_t need = 2 * tot + 2 * (size_t)c * c + 2 * c;
+    CALZ_TRY(small_scratch(ctx, need, &sm));
+    double *C1 = sm, *C2 = sm + tot, *nbef = C2 + tot, *naft = nbef + (size_t)c * c;
+    const int sweeps_max = doreorth ? 2 : 1;
+    bool second = false;
+    if (doreorth) {   // project.m:29-31 -- column norms before (diag of X'X)
+        CALZ_TRY(tsmm_tn(ctx, n, one_panel(X, ldX, c), X, ldX, c, nbef, c, true, nullptr, 0, true));
+    }
+    for (int sweep = 0; sweep < sweeps_max; ++sweep) {
+        double* C = sweep == 0 ? C1 : C2;
+        size_t off = 0;
+        for (int i = 0; i < nblk; ++i) {
+            if (empty_block(Qblk, mcols, i)) continue;
+            const int m = mcols[i];
+            CALZ_TRY(tsmm_tn(ctx, n, one_panel(Qblk[i], ldQ[i], m), X, ldX, c, C + off, m, false, nullptr, 0, true));
+            CALZ_TRY(ts_update(ctx, n, Qblk[i], ldQ[i], m, C + off, m, X, ldX, c, X, ldX, nullptr, 0));
+            off += (size_t)m * c;
+        }
+        if (!doreorth || sweep == 1) break;
+        // project.m:43-46 -- reorthogonalise when max(0.5*before - after) < 0  (criterion kept as written)
+        CALZ_TRY(tsmm_tn(ctx, n, one_panel(X, ldX, c), X, ldX, c, naft, c, true, nullptr, 0, true));
+        CALZ_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, nbef, (2 * (size_t)c * c) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        double worst = -1e300;
+        for (int j = 0; j < c; ++j) {
+            const double b = sqrt(ctx->pinned[(size_t)j * c + j]), a = sqrt(ctx->pinned[(size_t)c * c + (size_t)j * c + j]);
+            worst = std::max(worst, 0.5 * b - a);
+        }
+        second = worst < 0;
+        if (!second) break;
+    }
+    CALZ_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, sm, 2 * tot * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    size_t off = 0;
+    for (int i = 0; i < nblk; ++i) {
+        if (empty_block(Qblk, mcols, i)) continue;
+        const size_t cnt = (size_t)mcols[i] * c;
+        if (Rblk && Rblk[i])
+            for (size_t e = 0; e < cnt; ++e) Rblk[i][e] = ctx->pinned[off + e] + (second ? ctx->pinned[tot + off + e] : 0.0);
+        off += cnt;
+    }
+    return CALZ_OK;
+}
+
+int calz_project_and_normalize(calz_ctx* ctx, int64_t n, int nblk, const double* const* Qblk, const int64_t* ldQ,
+                               const int* mcols, int c, const double* X, int64_t ldX, int doreorth, int backend,
+                               double* QZ, int64_t ldQZ, double* const* Rblk, double* Rlast, int* second_pass, int* rank) {
+    if (!ctx || !X || !QZ || n < 1 || c < 1 || c > kMaxC || nblk < 0 || (backend != CALZ_QR_TSQR && backend != CALZ_QR_CHOLQR))
+        return set_error(ctx, CALZ_ERR_BADARG, "calz_project_and_normalize: bad arguments");
+    if (QZ == X) return set_error(ctx, CALZ_ERR_BADARG, "calz_project_and_normalize: QZ must not alias X");
+    CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    // ---- small device scratch
+    std::vector<int> blocks;
+    for (int i = 0; i < nblk; ++i)
+        if (!empty_block(Qblk, mcols, i)) blocks.push_back(i);
+    const int nb = (int)blocks.size();
+    const bool fuse_norms = doreorth && nb > 0;        // column norms of X ride along with the first coefficient sweep
+    size_t doubles = 8;                                // flags
+    std::vector<size_t> off1(nb), off2(nb);
+    std::vector<int> ld1(nb);
+    for (int k = 0; k < nb; ++k) {
+        const int m = mcols[blocks[k]];
+        ld1[k] = (k == 0 && fuse_norms) ? m + c : m;
+        off1[k] = doubles; doubles += (size_t)ld1[k] * c;
+    }
+    for (int k = 0; k < nb; ++k) { off2[k] = doubles; doubles += (size_t)mcols[blocks[k]] * c; }
+    const size_t offG = doubles; doubles += (size_t)c * c;
+    const size_t offR1 = doubles; doubles += (size_t)c * c;
+    const size_t offR2 = doubles; doubles += (size_t)c * c;
+    double* sm;
+    CALZ_TRY(small_scratch(ctx, doubles, &sm));
+    int* flags = (int*)sm;
+    CALZ_CUDA(ctx, cudaMemsetAsync(sm, 0, 8 * sizeof(double), ctx->stream));
+    double *G = sm + offG, *R1 = sm + offR1, *R2 = sm + offR2;
+
+    // ---- pass 1: Y = X - sum_i Q_i (Q_i' X)   (sequential over blocks, project.m:32-39); Y lives in QZ
+    const double* src = X;
+    int64_t ldsrc = ldX;
+    for (int k = 0; k < nb; ++k) {
+        const int i = blocks[k], m = mcols[i];
+        Panels A = one_panel(Qblk[i], ldQ[i], m);
+        if (k == 0 && fuse_norms) add_panel(A, X, ldX, c);          // [Q_1 X]' X: last c rows hold X'X
+        double* C = sm + off1[k];
+        CALZ_TRY(tsmm_tn(ctx, n, A, src, ldsrc, c, C, ld1[k], false, nullptr, 0, true));
+        CALZ_TRY(ts_update(ctx, n, Qblk[i], ldQ[i], m, C, ld1[k], src, ldsrc, c, QZ, ldQZ, nullptr, 0));
+        src = QZ;
+        ldsrc = ldQZ;
+    }
+    // nb2_i = ||X(:,i)||^2: diagonal of the X'X block of the fused sweep
+    const double* nb2 = nullptr;
+    int nb2_stride = 0;
+    if (fuse_norms) {
+        nb2 = sm + off1[0] + mcols[blocks[0]];
+        nb2_stride = ld1[0] + 1;
+    }
+    // ---- normalize(Y): R1 (+ the norm-drop decision on the device)
+    CALZ_TRY(factor_r(ctx, backend, n, c, src, ldsrc, G, R1, flags + 1, nb2, nb2_stride, flags + 0, nullptr, 0));
+
+    // ---- pass 2, predicated on flags[0] == 1 (projectAndNormalize.m:61-73): Z = Y - sum_i Q_i (Q_i' Y), in place
+    if (fuse_norms) {
+        for (int k = 0; k < nb; ++k) {
+            const int i = blocks[k], m = mcols[i];
+            double* C = sm + off2[k];
+            CALZ_TRY(tsmm_tn(ctx, n, one_panel(Qblk[i], ldQ[i], m), QZ, ldQZ, c, C, m, false, flags, 1, true));
+            CALZ_TRY(ts_update(ctx, n, Qblk[i], ldQ[i], m, C, m, QZ, ldQZ, c, QZ, ldQZ, flags, 1));
+        }
+        CALZ_TRY(factor_r(ctx, backend, n, c, QZ, ldQZ, G, R2, flags + 2, nullptr, 0, nullptr, flags, 1));
+    }
+    // ---- Q of the LAST normalize only
+    if (backend == CALZ_QR_CHOLQR) {
+        CALZ_TRY(ts_trsolve(ctx, n, c, src, ldsrc, R1, R2, flags, QZ, ldQZ));
+    } else {
+        // the reflectors on the device belong to the last factorisation that actually ran (Y, or Z if pass 2 fired)
+        CALZ_TRY(tsqr_form_q(ctx, n, c, src, ldsrc, QZ, ldQZ));
+    }
+
+    // ---- small results: one D2H copy, one synchronisation
+    CALZ_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, sm, doubles * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const double* h = ctx->pinned;
+    const int* hf = (const int*)h;
+    const bool second = hf[0] != 0;
+    const int info = second ? hf[2] : hf[1];
+    if (second_pass) *second_pass = second ? 1 : 0;
+    for (int k = 0; k < nb; ++k) {
+        const int i = blocks[k], m = mcols[i];
+        if (!Rblk || !Rblk[i]) continue;
+        for (int j = 0; j < c; ++j)
+            for (int a = 0; a < m; ++a) {
+                double v = h[off1[k] + (size_t)j * ld1[k] + a];
+                if (second) v = h[off2[k] + (size_t)j * m + a] + v;      // RZ{i} = RZ{i} + RY{i}  (:71-73)
+                Rblk[i][(size_t)j * m + a] = v;
+            }
+    }
+    const double* Rl = h + (second ? offR2 : offR1);
+    if (Rlast) memcpy(Rlast, Rl, (size_t)c * c * sizeof(double));
+    if (rank) *rank = numerical_rank(c, Rl, c, 1.0e-8);
+    if (info) return set_error(ctx, CALZ_ERR_CHOL, "projectAndNormalize/cholqr: Gram matrix not positive definite at pivot %d (pass %d)",
+                               info, second ? 2 : 1);
+    return CALZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------ host flavours
+namespace {
+struct Staged {
+    double* d = nullptr;
+    int64_t ld = 0;
+};
+int stage_in(calz_ctx* ctx, DevBuf& buf, int64_t n, int cols, const double* h, int64_t ldh, Staged* out, bool copy) {
+    out->ld = round_up(n, 32);
+    CALZ_TRY(reserve(ctx, buf, (size_t)out->ld * std::max(cols, 1) * sizeof(double)));
+    out->d = (double*)buf.p;
+    if (copy && cols > 0)
+        CALZ_CUDA(ctx, cudaMemcpy2DAsync(out->d, (size_t)out->ld * sizeof(double), h, (size_t)ldh * sizeof(double),
+                                         (size_t)n * sizeof(double), (size_t)cols, cudaMemcpyHostToDevice, ctx->stream));
+    return CALZ_OK;
+}
+int stage_out(calz_ctx* ctx, const Staged& s, int64_t n, int cols, double* h, int64_t ldh) {
+    CALZ_CUDA(ctx, cudaMemcpy2DAsync(h, (size_t)ldh * sizeof(double), s.d, (size_t)s.ld * sizeof(double),
+                                     (size_t)n * sizeof(double), (size_t)cols, cudaMemcpyDeviceToHost, ctx->stream));
+    CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CALZ_OK;
+}
+// all Q blocks of a cell array side by side in one staging buffer
+int stage_blocks(calz_ctx* ctx, DevBuf& buf, int64_t n, int nblk, const double* const* Qblk, const int64_t* ldQ,
+                 const int* mcols, std::vector<const double*>& dptr, std::vector<int64_t>& dld) {
+    int tot = 0;
+    for (int i = 0; i < nblk; ++i)
+        if (!empty_block(Qblk, mcols, i)) tot += mcols[i];
+    const int64_t ld = round_up(n, 32);
+    CALZ_TRY(reserve(ctx, buf, (size_t)ld * std::max(tot, 1) * sizeof(double)));
+    dptr.assign(nblk, nullptr);
+    dld.assign(nblk, ld);
+    int col = 0;
+    for (int i = 0; i < nblk; ++i) {
+        if (empty_block(Qblk, mcols, i)) continue;
+        double* d = (double*)buf.p + (size_t)col * ld;
+        CALZ_CUDA(ctx, cudaMemcpy2DAsync(d, (size_t)ld * sizeof(double), Qblk[i], (size_t)ldQ[i] * sizeof(double),
+                                         (size_t)n * sizeof(double), (size_t)mcols[i], cudaMemcpyHostToDevice, ctx->stream));
+        dptr[i] = d;
+        col += mcols[i];
+    }
+    return CALZ_OK;
+}
+}  // namespace
+
+int calz_tsqr_host(calz_ctx* ctx, int64_t n, int c, const double* A, int64_t ldA, double* Q, int64_t ldQ, double* R) {
+    if (!ctx || !A || !Q || !R || n < 1 || c < 1) return set_error(ctx, CALZ_ERR_BADARG, "calz_tsqr_host: bad arguments");
+    CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    Staged a, q;
+    CALZ_TRY(stage_in(ctx, ctx->work[1], n, c, A, ldA, &a, true));
+    CALZ_TRY(stage_in(ctx, ctx->work[2], n, c, nullptr, 0, &q, false));
+    CALZ_TRY(calz_tsqr(ctx, n, c, a.d, a.ld, q.d, q.ld, R));
+    return stage_out(ctx, q, n, c, Q, ldQ);
+}
+
+int calz_cholqr_host(calz_ctx* ctx, int64_t n, int c, const double* X, int64_t ldX, double* Q, int64_t ldQ, double* R, int* info) {
+    if (!ctx || !X || !Q || !R || n < 1 || c < 1) return set_error(ctx, CALZ_ERR_BADARG, "calz_cholqr_host: bad arguments");
+    CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    Staged a, q;
+    CALZ_TRY(stage_in(ctx, ctx->work[1], n, c, X, ldX, &a, true));
+    CALZ_TRY(stage_in(ctx, ctx->work[2], n, c, nullptr, 0, &q, false));
+    CALZ_TRY(calz_cholqr(ctx, n, c, a.d, a.ld, q.d, q.ld, R, info));
+    return stage_out(ctx, q, n, c, Q, ldQ);
+}
+
+int calz_normalize_host(calz_ctx* ctx, int64_t n, int c, const double* X, int64_t ldX, int backend, double tol, double* Q,
+                        int64_t ldQ, double* R, int* rank) {
+    if (!ctx || !X || !Q || !R || n < 1 || c < 1) return set_error(ctx, CALZ_ERR_BADARG, "calz_normalize_host: bad arguments");
+    CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    Staged a, q;
+    CALZ_TRY(stage_in(ctx, ctx->work[1], n, c, X, ldX, &a, true));
+    CALZ_TRY(stage_in(ctx, ctx->work[2], n, c, nullptr, 0, &q, false));
+    CALZ_TRY(calz_normalize(ctx, n, c, a.d, a.ld, backend, tol, q.d, q.ld, R, rank));
+    return stage_out(ctx, q, n, c, Q, ldQ);
+}
+
+int calz_project_host(calz_ctx* ctx, int64_t n, int nblk, const double* const* Qblk, const int64_t* ldQ, const int* mcols,
+                      int c, double* X, int64_t ldX, int doreorth, double* const* Rblk) {
+    if (!ctx || !X || n < 1 || c < 1) return set_error(ctx, CALZ_ERR_BADARG, "calz_project_host: bad arguments");
+    CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    Staged x;
+    std::vector<const double*> dq;
+    std::vector<int64_t> dld;
+    CALZ_TRY(stage_in(ctx, ctx->work[1], n, c, X, ldX, &x, true));
+    CALZ_TRY(stage_blocks(ctx, ctx->work[3], n, nblk, Qblk, ldQ, mcols, dq, dld));
+    CALZ_TRY(calz_project(ctx, n, nblk, dq.data(), dld.data(), mcols, c, x.d, x.ld, doreorth, Rblk));
+    return stage_out(ctx, x, n, c, X, ldX);
+}
+
+int calz_project_and_normalize_host(calz_ctx* ctx, int64_t n, int nblk, const double* const* Qblk, const int64_t* ldQ,
+                                    const int* mcols, int c, const double* X, int64_t ldX, int doreorth, int backend,
+                                    double* QZ, int64_t ldQZ, double* const* Rblk, double* Rlast, int* second_pass, int* rank) {
+    if (!ctx || !X || !QZ || n < 1 || c < 1) return set_error(ctx, CALZ_ERR_BADARG, "calz_project_and_normalize_host: bad arguments");
+    CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    Staged x, q;
+    std::vector<const double*> dq;
+    std::vector<int64_t> dld;
+    CALZ_TRY(stage_in(ctx, ctx->work[1], n, c, X, ldX, &x, true));
+    CALZ_TRY(stage_in(ctx, ctx->work[2], n, c, nullptr, 0, &q, false));
+    CALZ_TRY(stage_blocks(ctx, ctx->work[3], n, nblk, Qblk, ldQ, mcols, dq, dld));
+    int st = calz_project_and_normalize(ctx, n, nblk, dq.data(), dld.data(), mcols, c, x.d, x.ld, doreorth, backend, q.d, q.ld,
+                                        Rblk, Rlast, second_pass, rank);
+    if (st != CALZ_OK && st != CALZ_ERR_CHOL) return st;
+    int st2 = stage_out(ctx, q, n, c, QZ, ldQZ);
+    return st != CALZ_OK ? st : st2;
+}
+
+}  // extern "C"

@@ -1,0 +1,367 @@
+// K2/K3/K4/K8/K9/K10: tall-skinny fp64 kernels of the block orthogonalisation.
+//
+//   tsmm_tn     C = A'B  -- fp64 DMMA (mma.sync m8n8k4) contraction over the long dimension, deterministic
+//               two-stage reduction (per-CTA partials, last CTA sums them in a fixed order), all-reduce.
+//               Reference counterparts: cholqr.m:5 (G=X'*X), project.m:34 (R{i}=Q{i}'*X),
+//               projectAndNormalize.m:17-22 (column norms = diag of X'X, fused as an extra panel).
+//   ts_update   Y = X - Q*C              project.m:35
+//   chol_small  R = chol(G) on device    cholqr.m:6, plus the norm-drop test of projectAndNormalize.m:45-52
+//   ts_trsolve  Q = X/R                  cholqr.m:8
+#include <string.h>
+
+#include <algorithm>
+
+#include "tsops.cuh"
+
+namespace calz {
+
+// ------------------------------------------------------------------------------------------ DMMA
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ const double* panel_col(const Panels& P, int a) {
+    // column pointer of virtual column a (NULL past the end => zero fill)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        if (p < P.count) {
+            if (a < P.ncols[p]) return P.ptr[p] + (long long)a * P.ld[p];
+            a -= P.ncols[p];
+        }
+    }
+    return nullptr;
+}
+
+// C[a0 + 8*mt + g][b0 + 8*ct + ..] tiles; each warp streams 16 rows per iteration (4 DMMA k-steps).
+template <int MT, int CT, bool SAME>
+__global__ void __launch_bounds__(kTsThreads)
+k_tsmm_tn(long long n, Panels A, int a0, const double* __restrict__ B, long long ldB, int b0, int M, int c,
+          double* __restrict__ partials, double* __restrict__ C, int ldC, unsigned int* ticket,
+          const int* __restrict__ pred, int want) {
+    if (pred && *pred != want) return;
+    constexpr int WARPS = kTsThreads / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+
+    const double* acol[MT];
+    const double* bcol[CT];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+        int a = a0 + 8 * mt + g;
+        acol[mt] = (a < M) ? panel_col(A, a) : nullptr;
+    }
+#pragma unroll
+    for (int ct = 0; ct < CT; ++ct) {
+        int b = b0 + 8 * ct + g;
+        bcol[ct] = (b < c) ? B + (long long)b * ldB : nullptr;
+    }
+    double acc[MT][CT][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int ct = 0; ct < CT; ++ct) acc[mt][ct][0] = acc[mt][ct][1] = 0.0;
+
+    const long long stride = (long long)gridDim.x * WARPS * 16;
+    for (long long r0 = ((long long)blockIdx.x * WARPS + warp) * 16; r0 < n; r0 += stride) {
+        double av[MT][4], bv[CT][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long row = r0 + 4 * u + t;
+            const bool ok = row < n;
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) av[mt][u] = (ok && acol[mt]) ? __ldg(acol[mt] + row) : 0.0;
+            if (!SAME) {
+#pragma unroll
+                for (int ct = 0; ct < CT; ++ct) bv[ct][u] = (ok && bcol[ct]) ? __ldg(bcol[ct] + row) : 0.0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int ct = 0; ct < CT; ++ct)
+                    dmma_8x8x4(acc[mt][ct][0], acc[mt][ct][1], av[mt][u], SAME ? av[ct][u] : bv[ct][u]);
+    }
+
+    // ---- CTA reduction over warps (fixed order), then per-CTA partial tile to global
+    __shared__ double red[WARPS][MT * CT * 64];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int ct = 0; ct < CT; ++ct) {
+            double* tile = &red[warp][(mt * CT + ct) * 64];
+            tile[g * 8 + 2 * t] = acc[mt][ct][0];
+            tile[g * 8 + 2 * t + 1] = acc[mt][ct][1];
+        }
+    __syncthreads();
+    constexpr int TILE_ELEMS = MT * CT * 64;
+    double* mine = partials + (size_t)blockIdx.x * TILE_ELEMS;
+    for (int e = threadIdx.x; e < TILE_ELEMS; e += kTsThreads) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) s += red[w][e];
+        mine[e] = s;
+    }
+    __threadfence();
+    __shared__ bool is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int done = atomicAdd(ticket, 1u);
+        is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // ---- last CTA: one warp per output element, lanes stride over the CTAs, fixed shuffle tree
+    for (int e = warp; e < TILE_ELEMS; e += WARPS) {
+        const int tile = e >> 6, i = (e >> 3) & 7, j = e & 7;
+        const int mt = tile / CT, ct = tile % CT;
+        const int a = a0 + 8 * mt + i, b = b0 + 8 * ct + j;
+        if (a >= M || b >= c) continue;
+        double s = 0.0;
+        for (unsigned int blk = lane; blk < gridDim.x; blk += 32) s += __ldcg(partials + (size_t)blk * TILE_ELEMS + e);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) C[(size_t)b * ldC + a] = s;
+    }
+    if (threadIdx.x == 0) *ticket = 0;
+}
+
+// persistent grid: one wave of CTAs, as many as are co-resident (occupancy API), capped by the work
+template <class K>
+static int resident_grid(calz_ctx* ctx, K kernel, long long work_items) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTsThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    per_sm = (int)std::min<long long>(per_sm, ctx->opt_grid_mult);
+    long long grid = std::min<long long>((long long)ctx->num_sms * per_sm, work_items);
+    return (int)std::max<long long>(grid, 1);
+}
+
+template <int MT, int CT>
+static int launch_tsmm(calz_ctx* ctx, long long n, const Panels& A, int a0, const double* B, long long ldB, int b0,
+                       int M, int c, double* C, int ldC, bool same, const int* pred, int want) {
+    const bool sm = same && MT == CT;
+    const int grid = sm ? resident_grid(ctx, k_tsmm_tn<MT, CT, true>, (n + 127) / 128)
+                        : resident_grid(ctx, k_tsmm_tn<MT, CT, false>, (n + 127) / 128);
+    CALZ_TRY(reserve(ctx, ctx->partials, (size_t)grid * MT * CT * 64 * sizeof(double)));
+    double* part = (double*)ctx->partials.p;
+    if (sm)
+        k_tsmm_tn<MT, CT, true><<<grid, kTsThreads, 0, ctx->stream>>>(n, A, a0, B, ldB, b0, M, c, part, C, ldC, ctx->ticket, pred, want);
+    else
+        k_tsmm_tn<MT, CT, false><<<grid, kTsThreads, 0, ctx->stream>>>(n, A, a0, B, ldB, b0, M, c, part, C, ldC, ctx->ticket, pred, want);
+    CALZ_LAUNCH_CHECK(ctx);
+    return CALZ_OK;
+}
+
+int tsmm_tn(calz_ctx* ctx, int64_t n, const Panels& A, const double* B, int64_t ldB, int c, double* C_dev, int ldC,
+            bool same, const int* pred, int want, bool allreduce) {
+    const int M = A.total;
+    if (M <= 0 || c <= 0) return CALZ_OK;
+    // tile the (M x c) output: c in chunks of <= 32 columns, M in chunks of 64/CT columns
+    for (int b0 = 0; b0 < c; b0 += 32) {
+        const int cc = std::min(32, c - b0);
+        const int CT = (cc + 7) / 8;
+        const int mt_max = CT == 1 ? 8 : (CT == 2 ? 4 : 2);
+        for (int a0 = 0; a0 < M; a0 += 8 * mt_max) {
+            const int mm = std::min(8 * mt_max, M - a0);
+            int MT = 1;
+            while (8 * MT < mm) MT *= 2;
+            const bool sm = same && a0 == b0 && M == c;
+            int st;
+#define CALZ_TS(MTv, CTv) st = launch_tsmm<MTv, CTv>(ctx, n, A, a0, B, ldB, b0, M, c, C_dev, ldC, sm, pred, want)
+            if (CT == 1) { if (MT == 1) CALZ_TS(1, 1); else if (MT == 2) CALZ_TS(2, 1); else if (MT == 4) CALZ_TS(4, 1); else CALZ_TS(8, 1); }
+            else if (CT == 2) { if (MT == 1) CALZ_TS(1, 2); else if (MT == 2) CALZ_TS(2, 2); else CALZ_TS(4, 2); }
+            else if (CT == 3) { if (MT == 1) CALZ_TS(1, 3); else CALZ_TS(2, 3); }
+            else { if (MT == 1) CALZ_TS(1, 4); else CALZ_TS(2, 4); }
+#undef CALZ_TS
+            CALZ_TRY(st);
+        }
+    }
+    if (allreduce && ctx->nranks > 1) {
+        if (ldC != M) return set_error(ctx, CALZ_ERR_BADARG, "tsmm_tn: all-reduce needs a dense output (ldC == M)");
+        CALZ_TRY(allreduce_sum(ctx, C_dev, (size_t)M * c));
+    }
+    return CALZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------ update
+// One row per thread: y_j = x_j - sum_m q_m * C[m][j].  C is staged in shared memory (broadcast reads).
+template <int CT>
+__global__ void __launch_bounds__(kTsThreads)
+k_update(long long n, const double* __restrict__ Q, long long ldQ, int M, const double* __restrict__ C, int ldC,
+         const double* X, long long ldX, int c, double* Y, long long ldY, const int* __restrict__ pred, int want) {
+    if (pred && *pred != want) return;
+    constexpr int CW = 8 * CT;
+    constexpr int MCH = 64;
+    __shared__ double Cs[MCH][CW];
+    const long long stride = (long long)gridDim.x * kTsThreads;
+    const long long nround = (n + stride - 1) / stride * stride;
+    for (long long i = (long long)blockIdx.x * kTsThreads + threadIdx.x; i < nround; i += stride) {
+        const bool ok = i < n;
+        double y[CW];
+#pragma unroll
+        for (int j = 0; j < CW; ++j) y[j] = (ok && j < c) ? X[i + (long long)j * ldX] : 0.0;
+        for (int m0 = 0; m0 < M; m0 += MCH) {
+            const int mm = min(MCH, M - m0);
+            __syncthreads();
+            for (int e = threadIdx.x; e < mm * CW; e += kTsThreads) {
+                const int m = e / CW, j = e % CW;
+                Cs[m][j] = (j < c) ? C[(size_t)j * ldC + m0 + m] : 0.0;
+            }
+            __syncthreads();
+            if (ok) {
+#pragma unroll 4
+                for (int m = 0; m < mm; ++m) {
+                    const double q = __ldg(Q + i + (long long)(m0 + m) * ldQ);
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) y[j] = fma(-q, Cs[m][j], y[j]);
+                }
+            }
+        }
+        if (ok) {
+#pragma unroll
+            for (int j = 0; j < CW; ++j)
+                if (j < c) Y[i + (long long)j * ldY] = y[j];
+        }
+    }
+}
+
+int ts_update(calz_ctx* ctx, int64_t n, const double* Q, int64_t ldQ, int M, const double* C_dev, int ldC,
+              const double* X, int64_t ldX, int c, double* Y, int64_t ldY, const int* pred, int want) {
+    if (n <= 0 || c <= 0) return CALZ_OK;
+    if (c > kMaxC) return set_error(ctx, CALZ_ERR_UNSUPPORTED, "block width c=%d > %d", c, kMaxC);
+    const int CT = (c + 7) / 8;
+    int grid;
+#define CALZ_UP(CTv) grid = resident_grid(ctx, k_update<CTv>, (n + kTsThreads - 1) / kTsThreads); k_update<CTv><<<grid, kTsThreads, 0, ctx->stream>>>(n, Q, ldQ, M, C_dev, ldC, X, ldX, c, Y, ldY, pred, want)
+    if (CT == 1) { CALZ_UP(1); } else if (CT == 2) { CALZ_UP(2); } else if (CT == 3) { CALZ_UP(3); } else { CALZ_UP(4); }
+#undef CALZ_UP
+    CALZ_LAUNCH_CHECK(ctx);
+    return CALZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------ X / R
+// One row per thread, forward substitution along the row: q_j = (x_j - sum_{i<j} q_i R_ij) / R_jj.
+template <int CT>
+__global__ void __launch_bounds__(kTsThreads, (CT == 1 ? 4 : (CT == 2 ? 3 : 2)))
+k_trsolve(long long n, int c, const double* X, long long ldX, const double* __restrict__ Ra,
+          const double* __restrict__ Rb, const int* __restrict__ sel, double* Q, long long ldQ) {
+    constexpr int CW = 8 * CT;
+    __shared__ double Rs[CW][CW + 1];
+    const double* R = (sel && *sel) ? Rb : Ra;
+    for (int e = threadIdx.x; e < CW * CW; e += kTsThreads) {
+        const int i = e / CW, j = e % CW;
+        Rs[i][j] = (i < c && j < c) ? R[(size_t)j * c + i] : (i == j ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    // one row per thread, no grid-stride loop: keeps R in shared memory instead of 36..528 hoisted registers
+    const long long r = (long long)blockIdx.x * kTsThreads + threadIdx.x;
+    if (r < n) {
+        double q[CW];
+#pragma unroll
+        for (int j = 0; j < CW; ++j) q[j] = (j < c) ? X[r + (long long)j * ldX] : 0.0;
+#pragma unroll
+        for (int j = 0; j < CW; ++j) {
+            if (j < c) {
+                double s = q[j];
+#pragma unroll
+                for (int i = 0; i < j; ++i) s = fma(-q[i], Rs[i][j], s);
+                q[j] = s / Rs[j][j];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < CW; ++j)
+            if (j < c) Q[r + (long long)j * ldQ] = q[j];
+    }
+}
+
+int ts_trsolve(calz_ctx* ctx, int64_t n, int c, const double* X, int64_t ldX, const double* R_a, const double* R_b,
+               const int* sel, double* Q, int64_t ldQ) {
+    if (n <= 0 || c <= 0) return CALZ_OK;
+    if (c > kMaxC) return set_error(ctx, CALZ_ERR_UNSUPPORTED, "block width c=%d > %d", c, kMaxC);
+    const int CT = (c + 7) / 8;
+    int grid;
+    grid = (int)((n + kTsThreads - 1) / kTsThreads);
+#define CALZ_TR(CTv) k_trsolve<CTv><<<grid, kTsThreads, 0, ctx->stream>>>(n, c, X, ldX, R_a, R_b, sel, Q, ldQ)
+    if (CT == 1) { CALZ_TR(1); } else if (CT == 2) { CALZ_TR(2); } else if (CT == 3) { CALZ_TR(3); } else { CALZ_TR(4); }
+#undef CALZ_TR
+    CALZ_LAUNCH_CHECK(ctx);
+    return CALZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------ chol + decision
+__device__ void norm_drop_flag(int c, const double (*R)[kMaxC + 1], const double* nb2, int nb2_stride, int* flag_out, int lane) {
+    // projectAndNormalize.m:45-52: na_i = sqrt(sum(R(:,i).^2)); flag = max(|nb-na|./nb) > .5  (NaN skipped like MATLAB max)
+    double worst = 0.0;
+    if (lane < c) {
+        double s = 0.0;
+        for (int k = 0; k <= lane; ++k) s = fma(R[k][lane], R[k][lane], s);
+        const double na = sqrt(s), nb = sqrt(nb2[(size_t)lane * nb2_stride]);
+        const double rel = fabs(nb - na) / nb;
+        worst = (rel == rel) ? rel : 0.0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+    if (lane == 0) *flag_out = worst > 0.5 ? 1 : 0;
+}
+
+__global__ void k_chol_small(int c, const double* __restrict__ G, double* __restrict__ Rout, int* info_out,
+                             const double* __restrict__ nb2, int nb2_stride, int* flag_out,
+                             const int* __restrict__ pred, int want) {
+    if (pred && *pred != want) return;
+    __shared__ double A[kMaxC][kMaxC + 1];
+    const int lane = threadIdx.x;
+    for (int e = lane; e < c * c; e += 32) A[e % c][e / c] = G[e];     // A[i][j] = G(i,j)
+    __syncwarp();
+    int info = 0;
+    // right-looking upper Cholesky, lane l owns column l
+    for (int j = 0; j < c; ++j) {
+        const double d = A[j][j];
+        if (!(d > 0.0)) { info = j + 1; break; }
+        const double rjj = sqrt(d);
+        __syncwarp();
+        if (lane >= j && lane < c) A[j][lane] = (lane == j) ? rjj : A[j][lane] / rjj;
+        __syncwarp();
+        if (lane > j && lane < c) {
+            const double rjl = A[j][lane];
+            for (int i = j + 1; i <= lane; ++i) A[i][lane] = fma(-A[j][i], rjl, A[i][lane]);
+        }
+        __syncwarp();
+    }
+    for (int e = lane; e < c * c; e += 32) {
+        const int i = e % c, j = e / c;
+        Rout[e] = (i <= j) ? A[i][j] : 0.0;
+    }
+    if (lane == 0 && info_out) *info_out = info;
+    __syncwarp();
+    if (flag_out) {
+        if (info != 0) { if (lane == 0) *flag_out = 0; }
+        else norm_drop_flag(c, A, nb2, nb2_stride, flag_out, lane);
+    }
+}
+
+int chol_small(calz_ctx* ctx, int c, const double* G_dev, double* R_dev, int* info_out, const double* nb2,
+               int nb2_stride, int* flag_out, const int* pred, int want) {
+    if (c > kMaxC) return set_error(ctx, CALZ_ERR_UNSUPPORTED, "block width c=%d > %d", c, kMaxC);
+    k_chol_small<<<1, 32, 0, ctx->stream>>>(c, G_dev, R_dev, info_out, nb2, nb2_stride, nb2 ? flag_out : nullptr, pred, want);
+    CALZ_LAUNCH_CHECK(ctx);
+    return CALZ_OK;
+}
+
+__global__ void k_norm_drop(int c, const double* __restrict__ R, const double* __restrict__ nb2, int nb2_stride, int* flag_out) {
+    __shared__ double A[kMaxC][kMaxC + 1];
+    const int lane = threadIdx.x;
+    for (int e = lane; e < c * c; e += 32) A[e % c][e / c] = R[e];
+    __syncwarp();
+    norm_drop_flag(c, A, nb2, nb2_stride, flag_out, lane);
+}
+
+int norm_drop_decision(calz_ctx* ctx, int c, const double* R_dev, const double* nb2, int nb2_stride, int* flag_out) {
+    k_norm_drop<<<1, 32, 0, ctx->stream>>>(c, R_dev, nb2, nb2_stride, flag_out);
+    CALZ_LAUNCH_CHECK(ctx);
+    return CALZ_OK;
+}
+
+}  // namespace calz

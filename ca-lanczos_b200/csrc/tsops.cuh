@@ -1,0 +1,52 @@
+// Tall-skinny fp64 building blocks shared by the orthogonalisation entry points (tsops.cu, tsqr.cu).
+#pragma once
+#include "calz_internal.h"
+
+namespace calz {
+
+constexpr int kMaxC = 32;          // widest block being orthogonalised (s <= 31)
+constexpr int kTsThreads = 256;
+
+// A "panel list": virtual n x M matrix made of up to 4 column panels (a MATLAB cell array row, or [Q X]).
+struct Panels {
+    const double* ptr[4];
+    long long ld[4];
+    int ncols[4];
+    int count;
+    int total;
+};
+inline Panels one_panel(const double* p, int64_t ld, int ncols) {
+    Panels P{};
+    P.ptr[0] = p; P.ld[0] = ld; P.ncols[0] = ncols; P.count = 1; P.total = ncols;
+    return P;
+}
+inline void add_panel(Panels& P, const double* p, int64_t ld, int ncols) {
+    P.ptr[P.count] = p; P.ld[P.count] = ld; P.ncols[P.count] = ncols; P.count++; P.total += ncols;
+}
+
+// C = A'B (A = panel list n x M, B n x c) -> C_dev (M x c, leading dimension ldC), summed over ranks.
+// `pred`/`want`: if pred != NULL the kernels run only when *pred == want (device-side control flow).
+int tsmm_tn(calz_ctx* ctx, int64_t n, const Panels& A, const double* B, int64_t ldB, int c, double* C_dev,
+            int ldC, bool same, const int* pred, int want, bool allreduce);
+
+// Y = X - Q*C   (Q n x M single panel, C device M x c with ld ldC).  Y may alias X.
+int ts_update(calz_ctx* ctx, int64_t n, const double* Q, int64_t ldQ, int M, const double* C_dev, int ldC,
+              const double* X, int64_t ldX, int c, double* Y, int64_t ldY, const int* pred, int want);
+
+// Q = X / R  with R = *sel ? R_b : R_a (device c x c upper, ld c).  Q may alias X.
+int ts_trsolve(calz_ctx* ctx, int64_t n, int c, const double* X, int64_t ldX, const double* R_a,
+               const double* R_b, const int* sel, double* Q, int64_t ldQ);
+
+// R = chol(G) on the device (one warp), optional norm-drop decision of projectAndNormalize.m:45-52:
+// *flag_out = max_i |sqrt(nb2[i*nb2_stride]) - ||R(:,i)|| | / sqrt(nb2[...]) > 0.5.  info_out: 0 or failing pivot.
+int chol_small(calz_ctx* ctx, int c, const double* G_dev, double* R_dev, int* info_out, const double* nb2,
+               int nb2_stride, int* flag_out, const int* pred, int want);
+
+// same decision for a backend that already has R on the device (TSQR)
+int norm_drop_decision(calz_ctx* ctx, int c, const double* R_dev, const double* nb2, int nb2_stride, int* flag_out);
+
+// TSQR (tsqr.cu): R factor only / apply.  R_dev c x c upper with diag >= 0 (tsqr.m:9-11).
+int tsqr_factor(calz_ctx* ctx, int64_t n, int c, const double* A, int64_t ldA, double* R_dev, const int* pred, int want);
+int tsqr_form_q(calz_ctx* ctx, int64_t n, int c, const double* A, int64_t ldA, double* Q, int64_t ldQ);
+
+}  // namespace calz

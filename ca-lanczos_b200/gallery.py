@@ -1,0 +1,107 @@
+"""Synthetic input matrices for the CA-Lanczos hot path.
+
+All generators are rng-free or fixed-seed and return ``scipy.sparse.csr_matrix`` with
+sorted int32 column indices and fp64 values.  The reference's own scripts build their inputs the same
+way (``gallery('poisson',m)`` for C1, ``sparse(diag(linspace(1,10^k,N)))`` in
+``test_convergence_diagonal_matrices.m:16-19`` for C2); C3..C5 are the synthetic scale-ups named in
+BASELINE.json.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.sparse as sp
+
+
+def _stencil_csr(dims, diag):
+    """CSR of the (2*d+1)-point Dirichlet Laplacian stencil on a ``dims`` grid (first dim fastest).
+
+    Built directly in CSR (no COO/kron intermediate) so that 256^3 fits comfortably in host RAM.
+    """
+    dims = tuple(int(d) for d in dims)
+    n = int(np.prod(dims))
+    strides = np.cumprod((1,) + dims[:-1]).astype(np.int64)
+    idx = np.arange(n, dtype=np.int64)
+    coords = [(idx // st) % d for st, d in zip(strides, dims)]
+    # neighbour offsets in ascending column order: -s_d .. -s_1, 0, +s_1 .. +s_d
+    offs, valid = [], []
+    for k in reversed(range(len(dims))):
+        offs.append(-strides[k]); valid.append(coords[k] > 0)
+    offs.append(0); valid.append(np.ones(n, dtype=bool))
+    for k in range(len(dims)):
+        offs.append(strides[k]); valid.append(coords[k] < dims[k] - 1)
+    valid = np.stack(valid, axis=1)                      # n x (2d+1), row-major == CSR order
+    counts = valid.sum(axis=1)
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(counts, out=indptr[1:])
+    cols = (idx[:, None] + np.asarray(offs, dtype=np.int64)[None, :])[valid]
+    vals = np.where(np.asarray(offs) == 0, float(diag), -1.0)
+    data = np.broadcast_to(vals[None, :], valid.shape)[valid].astype(np.float64)
+    it = np.int32 if indptr[-1] < 2**31 else np.int64
+    A = sp.csr_matrix((data, cols.astype(np.int32), indptr.astype(it)), shape=(n, n))
+    A.has_sorted_indices = True
+    return A
+
+
+def poisson2d(m: int) -> sp.csr_matrix:
+    """``gallery('poisson',m)``: kron(I,T)+kron(T,I), T=tridiag(-1,2,-1); n=m^2 (C1: m=100)."""
+    return _stencil_csr((m, m), 4.0)
+
+
+def laplace3d(m: int, my: int | None = None, mz: int | None = None) -> sp.csr_matrix:
+    """7-point Dirichlet Laplacian on an m x my x mz grid, x fastest; diag 6, off -1 (C3: m=256)."""
+    my = m if my is None else my
+    mz = m if mz is None else mz
+    return _stencil_csr((m, my, mz), 6.0)
+
+
+def diag_linspace(n: int, K: float = 100.0) -> sp.csr_matrix:
+    """``sparse(diag(linspace(1,K,n)))`` (test_convergence_diagonal_matrices.m:16-19; C2: n=1e6, K=100)."""
+    d = np.linspace(1.0, float(K), int(n))
+    idx = np.arange(n, dtype=np.int32)
+    return sp.csr_matrix((d, idx, np.arange(n + 1, dtype=np.int32)), shape=(n, n))
+
+
+def powerlaw_spd(n: int, avg_deg: float = 20.0, seed: int = 0, alpha: float = 0.8) -> sp.csr_matrix:
+    """Symmetric power-law SPD matrix (C4): edges (i,j), i ~ Zipf-weighted rank^-alpha, j uniform,
+    symmetrised, values -U(0,1), diagonal = sum|row| + 1 (strictly diagonally dominant => SPD)."""
+    rng = np.random.default_rng(seed)
+    n = int(n)
+    m = int(n * avg_deg / 2)
+    w = np.arange(1, n + 1, dtype=np.float64) ** (-alpha)
+    cdf = np.cumsum(w); cdf /= cdf[-1]
+    i = np.searchsorted(cdf, rng.random(m)).astype(np.int64)
+    j = rng.integers(0, n, size=m, dtype=np.int64)
+    v = -rng.random(m)
+    keep = i != j
+    i, j, v = i[keep], j[keep], v[keep]
+    B = sp.coo_matrix((v, (i, j)), shape=(n, n)).tocsr()
+    B = B + B.T
+    B.sum_duplicates()
+    d = np.asarray(abs(B).sum(axis=1)).ravel() + 1.0
+    A = (B + sp.diags(d)).tocsr()
+    A.sort_indices()
+    A.indices = A.indices.astype(np.int32)
+    if A.indptr[-1] < 2**31:
+        A.indptr = A.indptr.astype(np.int32)
+    return A
+
+
+def _splitmix64(x: np.ndarray) -> np.ndarray:
+    x = (x + np.uint64(0x9E3779B97F4A7C15))
+    z = x
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def tall_skinny(n: int, c: int, seed: int = 0, row0: int = 0) -> np.ndarray:
+    """C5 input: n x c (Fortran order), entry (i,j) = U(-1,1) from splitmix64(seed, (row0+i)*c+j),
+    column j scaled by 2^-j.  Counter-based, so any row slice can be generated independently."""
+    with np.errstate(over="ignore"):
+        i = np.arange(row0, row0 + n, dtype=np.uint64)[:, None]
+        j = np.arange(c, dtype=np.uint64)[None, :]
+        ctr = (i * np.uint64(c) + j) + np.uint64(seed) * np.uint64(0xD1B54A32D192ED03)
+        bits = _splitmix64(ctr)
+    u = (bits >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
+    X = (2.0 * u - 1.0) * (2.0 ** -np.arange(c, dtype=np.float64))[None, :]
+    return np.asfortranarray(X)

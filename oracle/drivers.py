@@ -1,0 +1,275 @@
+"""CPU restatement of the CALLERS of the hot path (ca_lanczos / restarted_ca_lanczos, 'local' and 'full'
+orthogonalisation), needed only to carry parity from basis vectors through to T entries and Ritz values.
+TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED (see oracle/kernels.py).
+
+The block kernels are taken from a *kernel provider* ``K`` (default: oracle.kernels) exposing the
+reference's call surface -- ``matrix_powers_monomial``, ``matrix_powers_newton``, ``normalize``,
+``projectAndNormalize``, ``SpMV``.  The parity tests run the same driver once with the oracle provider and
+once with the CUDA drop-in provider and compare T, Q and the Ritz values (this is exactly the seam at
+which the reference's MATLAB drivers would pick up same-named MEX files).
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.linalg as sla
+
+from . import kernels as _oracle_kernels
+from .leja import leja, newton_basis_matrix
+
+
+def _mrdivide_upper(B, R):
+    """MATLAB ``B/R`` for square upper-triangular R (back substitution): X R = B."""
+    return sla.solve_triangular(R, B.T, trans="T", lower=False).T
+
+
+def _eyeshvec(n):
+    e = np.zeros(n); e[n - 1] = 1.0
+    return e
+
+
+# ----------------------------------------------------------------------------- lanczos.m
+def lanczos(A, r, maxiter, orth="local", K=_oracle_kernels):
+    """lanczos.m:18-60 + lanczos_basic :85-134 ('local' and 'full' = one CGS sweep, no renormalise
+    :62-66,112-114).  Returns (T, Q) like ``[T,Q] = lanczos(...)``."""
+    orth = str(orth).lower()
+    if orth not in ("local", "full"):
+        raise NotImplementedError("lanczos orth=%s is out of scope" % orth)
+    q = r / np.linalg.norm(r)
+    n = q.shape[0]
+    Q = np.zeros((n, maxiter + 1), order="F")
+    Q[:, 0] = q
+    alpha = np.zeros(maxiter); beta = np.zeros(maxiter)
+    for j in range(maxiter):
+        rr = K.SpMV(A, Q[:, j])
+        if j > 0:
+            rr = rr - beta[j - 1] * Q[:, j - 1]
+        alpha[j] = rr @ Q[:, j]
+        rr = rr - alpha[j] * Q[:, j]
+        beta[j] = np.sqrt(rr @ rr)
+        Q[:, j + 1] = rr / beta[j]
+        if orth == "full":
+            Rkk = Q[:, : j + 1].T @ Q[:, j + 1]
+            Q[:, j + 1] = Q[:, j + 1] - Q[:, : j + 1] @ Rkk
+    T = np.diag(alpha) + np.diag(beta[: maxiter - 1], 1) + np.diag(beta[: maxiter - 1], -1)
+    return T, Q
+
+
+def basis_matrix(A, q, s, basis, shift_orth, K=_oracle_kernels):
+    """ca_lanczos.m:61-72 / restarted_ca_lanczos.m:60-71 -- change-of-basis matrix Bk ((s+1) x s)."""
+    if basis.lower() == "monomial":
+        return np.asfortranarray(np.eye(s + 1)[:, 1 : s + 1])
+    if basis.lower() == "newton":
+        T, _ = lanczos(A, q, 2 * s, shift_orth, K=K)
+        basis_eigs = np.linalg.eigvalsh(T)          # T exactly symmetric => MATLAB eig = symmetric solver, ascending
+        basis_shifts, _ = leja(basis_eigs, "nonmodified")
+        return newton_basis_matrix(basis_shifts, s, 1)
+    raise ValueError("ERROR: Unknown basis type: " + basis)
+
+
+def _matrix_powers(A, q, s, Bk, basis, K):
+    """ca_lanczos.m:110-118."""
+    if basis.lower() == "monomial":
+        V = np.empty((q.shape[0], s + 1), order="F")
+        V[:, 0] = q
+        V[:, 1:] = K.matrix_powers_monomial(A, q, s)
+        return V
+    return K.matrix_powers_newton(A, q, s, np.diag(Bk).copy(), 1)
+
+
+def _extend_T(T, b, k, s, Bk, Rkk_s, Rk_s):
+    """ca_lanczos.m:200-223 (identical in restarted_ca_lanczos.m:336-359).  ``k`` is 1-based; b[k-1] is b(k)."""
+    Rkk = np.hstack([np.zeros((s, 1)), Rkk_s[:s, :]])
+    e1col = np.zeros((s + 1, 1)); e1col[0, 0] = 1.0
+    Rk = np.hstack([e1col, np.vstack([Rkk_s[s : s + 1, :s], Rk_s])])
+    zk = Rk[:s, s]
+    rho = Rk[s, s]
+    rho_t = Rk[s - 1, s - 1]
+    bk = Bk[s, s - 1]
+    e1 = np.zeros(s); e1[0] = 1.0
+    es = _eyeshvec(s)
+    Rss = Rk[:s, :s]
+    Tk = (_mrdivide_upper(Rss @ Bk[:s, :], Rss)
+          + (bk / rho_t) * np.outer(zk, es)
+          - _mrdivide_upper(((b[k - 2] * np.outer(e1, es)) @ Rkk[:, :s]), Rss))
+    b[k - 1] = bk * (rho / rho_t)
+    m = s * (k - 1)
+    Tn = np.zeros((m + s + 1, m + s), order="F")
+    Tn[:m, :m] = T[:m, :m]
+    Tn[m - 1, m] = b[k - 2]                       # T12 = b(k-1) * e_last * e1'
+    Tn[m, m - 1] = b[k - 2]                       # T21 = b(k-1) * e1 * e_last'
+    Tn[m : m + s, m : m + s] = Tk
+    Tn[m + s, m + s - 1] = b[k - 1]               # T32 = b(k) * es'
+    return Tn
+
+
+# ----------------------------------------------------------------------------- ca_lanczos.m
+def ca_lanczos(A, r, s, iter, basis, orth="local", K=_oracle_kernels, backend="tsqr", Bk=None, info=None):
+    """ca_lanczos.m:24-86 + ca_lanczos_basic :150-245 ('local' and 'full').  Returns (T, Q)."""
+    orth = str(orth).lower()
+    if orth not in ("local", "full"):
+        raise NotImplementedError("ca_lanczos orth=%s is out of scope" % orth)
+    t = int(np.ceil(iter / s))
+    q = r / np.sqrt(r @ r)
+    if Bk is None:
+        Bk = basis_matrix(A, q, s, basis, "full", K=K)
+    n = q.shape[0]
+    Q = np.zeros((n, t * s + 1), order="F")
+    Q[:, 0] = q
+    b = np.zeros(t + 1)
+    T = None
+    log = []
+    for k in range(1, t + 1):
+        if k > 1:
+            q = Q[:, (k - 1) * s]
+        V = _matrix_powers(A, q, s, Bk, basis, K)
+        if k == 1:
+            Q[:, : s + 1], Rk, _ = K.normalize(V[:, : s + 1], backend=backend)
+            T = _mrdivide_upper(Rk @ Bk, Rk[:s, :s])
+            b[0] = T[s, s - 1]
+        else:
+            inf = {}
+            Q_, Rk_ = K.projectAndNormalize([Q[:, (k - 2) * s : (k - 1) * s + 1]], V[:, 1 : s + 1], True,
+                                            backend=backend, info=inf)
+            log.append(inf)
+            Rkk_s, Rk_s = Rk_[0], Rk_[1]
+            Q[:, (k - 1) * s + 1 : k * s + 1] = Q_
+            if orth == "full":
+                Q[:, (k - 1) * s + 1 : k * s + 1], _ = K.projectAndNormalize(
+                    [Q[:, : (k - 1) * s + 1]], Q[:, (k - 1) * s + 1 : k * s + 1], True, backend=backend)
+            T = _extend_T(T, b, k, s, Bk, Rkk_s, Rk_s)
+    if info is not None:
+        info["pan"] = log
+        info["Bk"] = Bk
+    return np.asfortranarray(T[: s * t, : s * t]), Q[:, : s * t]
+
+
+# ----------------------------------------------------------------------------- restarted_ca_lanczos.m
+def normest(S, tol=1.0e-6):
+    """MATLAB ``normest`` (restarted_ca_lanczos.m:35): power iteration on S'S started from the column sums."""
+    x = np.asarray(abs(S).sum(axis=0)).ravel().astype(np.float64)
+    e = np.linalg.norm(x)
+    if e == 0:
+        return e
+    x = x / e
+    e0 = 0.0
+    cnt = 0
+    while abs(e - e0) > tol * e:
+        e0 = e
+        Sx = S @ x
+        x = S.T @ Sx
+        normx = np.linalg.norm(x)
+        e = normx / np.linalg.norm(Sx)
+        x = x / normx
+        cnt += 1
+        if cnt > 100:
+            break
+    return e
+
+
+def _restarted_lanczos_basic(A, Q_conv, q, Bk, maxiter, s, basis, orth, K, backend):
+    """restarted_ca_lanczos.m:288-367 -- note ``while k <= maxiter`` => maxiter+1 blocks (:301)."""
+    n = q.shape[0]
+    nblk = maxiter + 1
+    Q = np.zeros((n, nblk * s + 1), order="F")
+    Q[:, 0] = q
+    b = np.zeros(nblk + 1)
+    T = None
+    Qc = None if (Q_conv is None or np.size(Q_conv) == 0) else Q_conv
+    for k in range(1, nblk + 1):
+        if k > 1:
+            q = Q[:, (k - 1) * s]
+        V = _matrix_powers(A, q, s, Bk, basis, K)
+        if k == 1:
+            Q_, Rk, _ = K.normalize(V[:, : s + 1], backend=backend)
+            Q[:, : s + 1], _ = K.projectAndNormalize([Qc], Q_, True, backend=backend)
+            T = _mrdivide_upper(Rk @ Bk, Rk[:s, :s])
+            b[0] = T[s, s - 1]
+        else:
+            Qprev = Q[:, (k - 2) * s : (k - 1) * s + 1]
+            if orth == "local":
+                Q_, Rk_ = K.projectAndNormalize([Qprev, Qc], V[:, 1 : s + 1], True, backend=backend)
+                Q[:, (k - 1) * s + 1 : k * s + 1] = Q_
+                Rkk_s, Rk_s = Rk_[0], Rk_[2]
+            else:
+                Q_, Rk_ = K.projectAndNormalize([Qprev], V[:, 1 : s + 1], True, backend=backend)
+                Rkk_s, Rk_s = Rk_[0], Rk_[1]
+                Qold = Q[:, : (k - 2) * s] if (k - 2) * s > 0 else None
+                Q[:, (k - 1) * s + 1 : k * s + 1], _ = K.projectAndNormalize([Qc, Qold], Q_, True, backend=backend)
+            T = _extend_T(T, b, k, s, Bk, Rkk_s, Rk_s)
+    kk = nblk
+    return Q[:, : s * (kk - 1)], np.asfortranarray(T[: s * (kk - 1) + 1, : s * (kk - 1)])
+
+
+def restarted_ca_lanczos(A, r, max_lanczos, n_wanted_eigs=10, s=6, basis="newton", orth="local", tol=1.0e-8,
+                         K=_oracle_kernels, backend="tsqr", max_restarts=200):
+    """restarted_ca_lanczos.m:4-202 ('local' and 'full'; restart strategy 'largest' :52,:204-248).
+
+    Returns (conv_eigs, Q_conv, num_restarts, rnorms, orth_err).
+    """
+    orth = str(orth).lower()
+    if orth not in ("local", "full"):
+        raise NotImplementedError("restarted_ca_lanczos orth=%s is out of scope" % orth)
+    norm_A = normest(A)
+    tol = tol * norm_A
+    n = r.shape[0]
+    q = r / np.linalg.norm(r)
+    Bk = basis_matrix(A, q, s, basis, "local", K=K)
+    Q = np.zeros((n, max_lanczos + n_wanted_eigs + s * (max_lanczos // s)), order="F")
+    Q_conv = None
+    conv_eigs, conv_rnorms = [], []
+    rnorms = np.zeros((max_restarts, n_wanted_eigs))
+    orth_err = []
+    num_restarts = 0
+    restart = True
+    nconv = 0
+    while restart and num_restarts < max_restarts:
+        num_restarts += 1
+        iters = max_lanczos // s
+        if iters == 0:
+            break                                   # reference branch uses undefined variables (:91-95)
+        Q_new, T = _restarted_lanczos_basic(A, Q_conv, q, Bk, iters, s, basis,
+                                            "local" if orth == "local" else "fro", K, backend)
+        m = s * iters
+        Dp, Vp = np.linalg.eig(T[:m, :m])           # non-symmetric T => general solver (Appendix B)
+        Dp = np.real(Dp).copy(); Vp = np.real(Vp).copy()
+        beta = T[m, m - 1]
+        ritz_norms = beta * np.abs(Vp[m - 1, :])
+        k = 0
+        for i in range(m):
+            if ritz_norms[i] < tol:
+                Dp[[i, k]] = Dp[[k, i]]
+                Vp[:, [i, k]] = Vp[:, [k, i]]
+                ritz_norms[[i, k]] = ritz_norms[[k, i]]
+                k += 1
+        for i in range(k):
+            Q[:, nconv + i] = Q_new @ Vp[:, i]
+            conv_eigs.append(Dp[i]); conv_rnorms.append(ritz_norms[i])
+        if num_restarts > 1:
+            rnorms[num_restarts - 1, :nconv] = rnorms[num_restarts - 2, :nconv]
+        for i in range(k):
+            if nconv + i < n_wanted_eigs:
+                l = conv_eigs[nconv + i]; x = Q[:, nconv + i]
+                rnorms[num_restarts - 1, nconv + i] = np.linalg.norm(A @ x - l * x) / np.linalg.norm(l * x)
+        rest = Dp[k:]
+        ix = np.argsort(-rest, kind="stable")
+        for i in range(max(0, n_wanted_eigs - nconv - k)):
+            l = rest[ix[i]]; x = Q_new @ Vp[:, k + ix[i]]
+            rnorms[num_restarts - 1, nconv + i + k] = np.linalg.norm(A @ x - l * x) / np.linalg.norm(l * x)
+        Qall = Q_new if Q_conv is None else np.hstack([Q_conv, Q_new])
+        orth_err.append(np.linalg.norm(np.eye(Qall.shape[1]) - Qall.T @ Qall, "fro"))
+        nconv += k
+        Q_conv = np.asfortranarray(Q[:, :nconv]) if nconv > 0 else None
+        restart = not (len(conv_eigs) >= n_wanted_eigs)
+        if restart:
+            l = k                                  # generateStartVector 'largest' (:209-218)
+            for j in range(k, m):
+                if Dp[j] > Dp[l]:
+                    l = j
+            q = Q_new @ Vp[:, l]
+            q = q / np.linalg.norm(q)
+    conv_eigs = np.asarray(conv_eigs); conv_rnorms = np.asarray(conv_rnorms)
+    ixs = np.argsort(-conv_eigs, kind="stable")
+    keep = n_wanted_eigs if not restart else nconv
+    conv_eigs = conv_eigs[ixs][:keep]
+    Qc = Q_conv[:, ixs][:, :keep] if Q_conv is not None else np.zeros((n, 0))
+    return conv_eigs, Qc, num_restarts, rnorms[:num_restarts], np.asarray(orth_err)

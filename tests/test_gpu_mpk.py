@@ -1,0 +1,151 @@
+"""GPU parity tests of the matrix powers kernel (K1) against the oracle, through the C ABI (ctypes).
+
+Tolerance: basis vectors within 1e-10 relative (north_star); the SpMV sums differ from the oracle only by
+fma contraction / summation order, so the tests assert a much tighter 1e-13 per column (2-norm relative).
+"""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+from ca_lanczos_b200 import api, gallery  # noqa: E402
+from oracle import kernels  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-13
+
+
+def relcols(A, B):
+    return float(np.max(np.linalg.norm(A - B, axis=0) / np.maximum(np.linalg.norm(B, axis=0), 1e-300)))
+
+
+def _random_sym(n, deg, seed):
+    rng = np.random.default_rng(seed)
+    B = sp.random(n, n, density=deg / n, random_state=rng, format="csr", data_rvs=lambda k: rng.standard_normal(k))
+    A = (B + B.T + sp.diags(rng.standard_normal(n))).tocsr()
+    A.sort_indices()
+    return A
+
+
+MATS = {
+    "poisson100": lambda: gallery.poisson2d(100),                 # C1
+    "diag20000": lambda: gallery.diag_linspace(20000, 100.0),     # C2 (scaled)
+    "lap3d": lambda: gallery.laplace3d(40, 24, 33),               # C3 (scaled, non-cubic, n not a multiple of 32)
+    "random": lambda: _random_sym(5003, 9, 7),                    # ragged rows incl. empty ones
+    "powerlaw": lambda: gallery.powerlaw_spd(20000, 8.0, seed=0),  # C4 (scaled): very long and very short rows
+    "tiny": lambda: gallery.poisson2d(3),                         # n=9 < one SELL slice
+}
+
+
+@pytest.mark.parametrize("layout", ["csr", "sell"])
+@pytest.mark.parametrize("name", list(MATS))
+def test_spmv_and_monomial(name, layout):
+    A = MATS[name]()
+    n = A.shape[0]
+    dm = api.DeviceMatrix(A, s_max=8, layout=layout)
+    assert dm.layout == layout
+    q = np.cos(0.1 * np.arange(n)) + 1.5
+    np.testing.assert_allclose(api.SpMV(dm, q), A @ q, rtol=0, atol=TOL * np.linalg.norm(A @ q, np.inf) + 1e-300)
+    s = 5
+    V = api.matrix_powers_monomial(dm, q / np.linalg.norm(q), s)
+    Vo = kernels.matrix_powers_monomial(A, q / np.linalg.norm(q), s)
+    assert V.shape == (n, s)                                      # q itself is NOT returned
+    assert relcols(V, Vo) < TOL
+    dm.close()
+
+
+@pytest.mark.parametrize("layout", ["csr", "sell", "auto"])
+@pytest.mark.parametrize("name", ["poisson100", "diag20000", "lap3d", "random"])
+def test_newton_basis(name, layout):
+    A = MATS[name]()
+    n = A.shape[0]
+    s = 8
+    lam = np.array([99.6, 1.4, 45.8, 81.1, 19.9, 64.5, 7.6, 93.4]) * (8.0 / 100.0 if name != "diag20000" else 1.0)
+    v = np.ones(n) / np.sqrt(n)
+    V = api.matrix_powers_newton(A if layout == "auto" else api.DeviceMatrix(A, 8, layout), v, s, lam, 1)
+    Vo = kernels.matrix_powers_newton(A, v, s, lam, 1)
+    assert V.shape == (n, s + 1)
+    np.testing.assert_array_equal(V[:, 0], v)                     # start vector is column 1
+    assert relcols(V, Vo) < TOL
+    V0 = api.matrix_powers_newton(A, v, s, lam)                   # modifiedp defaults to 0 (:16-18): same for real shifts
+    assert relcols(V0, Vo) < TOL
+
+
+def test_newton_complex_pair_and_errors():
+    A = gallery.poisson2d(30)
+    v = np.sin(np.arange(900.0)) + 2
+    lam = np.array([3 + 0.5j, 3 - 0.5j, 1.0, 6 + 2j, 6 - 2j])
+    V = api.matrix_powers_newton(A, v, 5, lam, 1)
+    assert relcols(V, kernels.matrix_powers_newton(A, v, 5, lam, 1)) < TOL
+    with pytest.raises(ValueError):                               # matrix_powers_newton.m:36-39
+        api.matrix_powers_newton(A, v, 2, np.array([3 - 0.5j, 3 + 0.5j]), 1)
+    with pytest.raises(api.CalzError):                            # complex vectors are out of scope
+        api.matrix_powers_newton(A, v, 2, np.array([3 - 0.5j, 3 + 0.5j]), 0)
+    with pytest.raises(ValueError):
+        api.matrix_powers_newton(A, v[:-1], 2, lam, 1)
+
+
+def test_csc_ingest_of_nonsymmetric_matrix():
+    # the MEX gateways hand MATLAB's CSC arrays to calz_mat_create_csc64, which transposes on the host
+    import ctypes as C
+    from ca_lanczos_b200 import _lib
+    rng = np.random.default_rng(3)
+    A = sp.random(700, 700, density=0.01, random_state=rng, format="csc") + sp.eye(700, format="csc") * 2
+    A = A.tocsc(); A.sort_indices()
+    ctx = api.default_context()
+    jc = A.indptr.astype(np.uint64); ir = A.indices.astype(np.uint64); pr = A.data.astype(np.float64)
+    h = C.c_void_p()
+    _lib.check(ctx.lib.calz_mat_create_csc64(ctx.h, 700, jc.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                             ir.ctypes.data_as(C.POINTER(C.c_uint64)), pr.ctypes.data_as(_lib.c_dp), 4, 0,
+                                             C.byref(h)), ctx.h)
+    x = rng.standard_normal(700); y = np.empty(700)
+    _lib.check(ctx.lib.calz_spmv_host(h, x.ctypes.data_as(_lib.c_dp), y.ctypes.data_as(_lib.c_dp)), ctx.h)
+    np.testing.assert_allclose(y, A @ x, rtol=1e-13, atol=1e-13)
+    ctx.lib.calz_mat_destroy(h)
+
+
+@pytest.mark.parametrize("chunk", [1 << 16, 1 << 20])
+def test_l2_temporal_blocking_is_bit_identical(chunk):
+    # the skewed chunk schedule only reorders launches: results must not change by a single bit
+    A = gallery.laplace3d(32, 32, 64)
+    v = np.ones(A.shape[0]) / np.sqrt(A.shape[0])
+    lam = np.array([11.9, 0.2, 6.0, 9.0, 3.0, 7.5])
+    ctx = api.default_context()
+    dm = api.DeviceMatrix(A, 6, "sell")
+    V0 = api.matrix_powers_newton(dm, v, 6, lam, 1)
+    ctx.set_option("mpk_l2_chunk_bytes", chunk)
+    try:
+        V1 = api.matrix_powers_newton(dm, v, 6, lam, 1)
+    finally:
+        ctx.set_option("mpk_l2_chunk_bytes", 0)
+    np.testing.assert_array_equal(V0, V1)
+    assert relcols(V0, kernels.matrix_powers_newton(A, v, 6, lam, 1)) < TOL
+
+
+@pytest.mark.parametrize("name", ["c1_poisson_s4_monomial", "c2_diag_s8_newton"])
+def test_mpk_against_committed_goldens(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    A = gallery.poisson2d(int(g["m"])) if "poisson" in name else gallery.diag_linspace(int(g["n"]), 100.0)
+    r = np.ones(A.shape[0]); q = r / np.sqrt(r @ r)
+    s = int(g["s"])
+    if str(g["basis"]) == "newton":
+        V = api.matrix_powers_newton(A, q, s, g["shifts"], 1)
+    else:
+        V = np.column_stack([q, api.matrix_powers_monomial(A, q, s)])
+    assert relcols(V[g["rows"]], g["V_rows"]) < 1e-12
+
+
+def test_full_size_c2_basis_identity():
+    # C2 at BASELINE size (n = 1e6): size-independent property  A V(:,1:s) = V(:,1:s+1) B  (newton_basis_matrix.m:3-4)
+    n, s = 1_000_000, 8
+    A = gallery.diag_linspace(n, 100.0)
+    lam = np.array([99.5677, 1.4323, 45.7883, 81.1407, 19.8593, 64.4648, 7.5729, 93.4271])
+    v = np.ones(n) / np.sqrt(n)
+    V = api.matrix_powers_newton(A, v, s, lam, 1)
+    B = np.zeros((s + 1, s)); B[np.arange(s), np.arange(s)] = lam; B[np.arange(1, s + 1), np.arange(s)] = 1
+    assert np.linalg.norm(A @ V[:, :s] - V @ B) <= 1e-13 * np.linalg.norm(V)
+    d = np.linspace(1, 100, n)                                    # diagonal A: closed form prod(d - lam_i) * v
+    np.testing.assert_allclose(V[:, s], np.prod(d[:, None] - lam[None, :], axis=1) * v, rtol=1e-12, atol=1e-3 * 1e-12)

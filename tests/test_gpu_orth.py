@@ -1,0 +1,178 @@
+"""GPU parity tests of the block orthogonalisation (tsqr / cholqr / normalize / project / projectAndNormalize)
+against the oracle, through the C ABI.
+
+Tolerances (written out as north_star asks): R factors and coefficient blocks within 1e-10 relative (norm-wise),
+basis vectors within 1e-10 relative per column scaled by the conditioning of the block where the QR itself is
+ill-conditioned (two backward-stable QRs of the same block differ by ~kappa*eps), orthogonality no worse than
+the oracle's.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from ca_lanczos_b200 import api, gallery  # noqa: E402
+from oracle import kernels  # noqa: E402
+
+EPS = 2.2e-16
+
+
+def rel(A, B):
+    return float(np.linalg.norm(A - B) / max(np.linalg.norm(B), 1e-300))
+
+
+def orth(Q):
+    return float(np.linalg.norm(Q.T @ Q - np.eye(Q.shape[1])))
+
+
+SHAPES = [(1, 1), (7, 3), (33, 5), (128, 8), (129, 8), (1000, 1), (4097, 9), (50000, 8), (30011, 13), (20000, 17), (9000, 32)]
+
+
+@pytest.mark.parametrize("n,c", SHAPES)
+def test_tsqr(n, c):
+    X = gallery.tall_skinny(n, c, seed=n + c)
+    if n < c:
+        pytest.skip("tall-skinny only")
+    Q, R = api.tsqr(X)
+    Qo, Ro = kernels.tsqr(X)
+    kappa = np.linalg.cond(X) if n >= c else 1.0
+    assert np.all(np.diag(R) >= 0) and np.allclose(np.tril(R, -1), 0, atol=0)
+    assert rel(R, Ro) < max(1e-10, 0) and rel(R, Ro) < 100 * kappa * EPS
+    assert rel(Q @ R, X) < 1e-14 * np.sqrt(c) * 10
+    assert orth(Q) < 1e-14 * c * 10                               # Householder: orthogonal to machine precision
+    assert rel(Q, Qo) < 100 * kappa * EPS
+
+
+def test_tsqr_zero_column_sign_zero():
+    X = gallery.tall_skinny(500, 3, seed=2); X[:, 1] = 0.0
+    Q, R = api.tsqr(X)
+    Qo, Ro = kernels.tsqr(X)
+    assert R[1, 1] == 0.0 and np.all(Q[:, 1] == 0.0)              # sign(0) = 0 (tsqr.m:9)
+    assert rel(R, Ro) < 1e-13
+
+
+@pytest.mark.parametrize("n,c", SHAPES)
+def test_cholqr(n, c):
+    if n < 4 * c:
+        pytest.skip("Gram matrix singular")
+    X = gallery.tall_skinny(n, c, seed=n + c)
+    kappa = np.linalg.cond(X)
+    Q, R = api.cholqr(X)
+    Qo, Ro = kernels.cholqr(X)
+    assert np.all(np.diag(R) > 0) and np.allclose(np.tril(R, -1), 0, atol=0)
+    assert rel(R, Ro) < 100 * kappa ** 2 * EPS
+    assert rel(Q @ R, X) < 1e-13
+    assert orth(Q) < 100 * kappa ** 2 * EPS
+    assert rel(Q, Qo) < 100 * kappa ** 2 * EPS
+
+
+def test_cholqr_not_positive_definite_raises():
+    X = np.ones((1000, 3), order="F")
+    with pytest.raises(np.linalg.LinAlgError):
+        api.cholqr(X)
+
+
+@pytest.mark.parametrize("backend", ["tsqr", "cholqr"])
+def test_normalize_rank(backend):
+    X = gallery.tall_skinny(3000, 5, seed=1)
+    Q, R, rank = api.normalize(X, backend=backend)
+    assert rank == 5 and rel(R, kernels.normalize(X, backend=backend)[1]) < 1e-10
+    if backend == "tsqr":
+        X[:, 4] = 3 * X[:, 1] + 1e-13 * X[:, 2]
+        assert api.normalize(X, backend=backend)[2] == kernels.normalize(X, backend=backend)[2] == 4
+    with pytest.raises(NotImplementedError):
+        api.normalize(X, "randomizeNullSpace")
+
+
+def _orthobasis(n, m, seed):
+    return kernels.tsqr(gallery.tall_skinny(n, m, seed=seed))[0]
+
+
+@pytest.mark.parametrize("n,ms,c", [(5000, [5], 4), (40001, [9], 8), (3000, [9, 0, 20], 6), (2500, [70], 8), (2000, [3, 130], 17)])
+def test_project(n, ms, c):
+    Q = []
+    for i, m in enumerate(ms):
+        if m == 0:
+            Q.append(None)
+            continue
+        B = gallery.tall_skinny(n, m, seed=100 + i)
+        B, _ = kernels.project([q for q in Q if q is not None], B)
+        Q.append(kernels.tsqr(B)[0])
+    X = gallery.tall_skinny(n, c, seed=7)
+    Y, R = api.project(Q, X)
+    Yo, Ro = kernels.project(Q, X)
+    assert rel(Y, Yo) < 1e-13
+    for r, ro in zip(R, Ro):
+        assert (r is None) == (ro is None)
+        if r is not None:
+            assert rel(r, ro) < 1e-13
+    assert api.project([], X)[1] == []
+    with pytest.raises(TypeError):
+        api.project(Q[0], X)                                       # project.m:12-15
+
+
+def test_project_doreorth_branch():
+    n = 4000
+    Q = [_orthobasis(n, 6, 1)]
+    X = Q[0] @ np.ones((6, 3)) + 1e-6 * gallery.tall_skinny(n, 3, seed=3)
+    for Xi in (X, gallery.tall_skinny(n, 3, seed=4)):
+        Y, R = api.project(Q, Xi, True)
+        Yo, Ro = kernels.project(Q, Xi, True)
+        assert rel(R[0], Ro[0]) < 1e-12
+        assert np.linalg.norm(Y - Yo) <= 1e-12 * np.linalg.norm(Xi)
+
+
+@pytest.mark.parametrize("backend", ["cholqr", "tsqr"])
+@pytest.mark.parametrize("n,ms,c", [(6000, [5], 4), (50000, [9], 8), (4000, [9, 12], 8), (3000, [], 5), (3000, [0], 5), (7000, [17], 16)])
+def test_project_and_normalize(backend, n, ms, c):
+    Q = []
+    for i, m in enumerate(ms):
+        Q.append(None if m == 0 else kernels.tsqr(kernels.project([q for q in Q if q is not None],
+                                                                  gallery.tall_skinny(n, m, seed=200 + i))[0])[0])
+    real = [q for q in Q if q is not None]
+    far = gallery.tall_skinny(n, c, seed=9)
+    cases = [(far, False)]
+    if real:
+        near = real[0] @ np.ones((real[0].shape[1], c)) + 1e-2 * gallery.tall_skinny(n, c, seed=10)
+        cases.append((near, True))
+    for X, want_second in cases:
+        info, info_o = {}, {}
+        QZ, RZ = api.projectAndNormalize(Q, X, True, backend=backend, info=info)
+        QZo, RZo = kernels.projectAndNormalize(Q, X, True, backend=backend, info=info_o)
+        assert info["second_pass"] == info_o["second_pass"] == want_second
+        assert info["rank"] == info_o["rank"]
+        assert len(RZ) == len(Q) + 1
+        kappa = np.linalg.cond(RZo[-1])
+        tolR = 1e-10 if backend == "tsqr" else max(1e-10, 100 * kappa ** 2 * EPS)
+        for r, ro in zip(RZ, RZo):
+            assert (r is None) == (ro is None)
+            if r is not None:
+                assert rel(r, ro) < tolR
+        assert rel(QZ, QZo) < tolR
+        rec = sum((q @ r for q, r in zip(Q, RZ) if q is not None), np.zeros_like(X)) + QZ @ RZ[-1]
+        assert rel(rec, X) < 1e-13                                 # reconstruction identity (Appendix B)
+        assert orth(QZ) <= max(10 * orth(QZo), 1e-13)              # orthogonality no worse than the oracle
+        for q in real:
+            assert np.linalg.norm(q.T @ QZ) < 1e-11
+
+
+def test_pan_without_reorth():
+    n = 3000
+    Q = [_orthobasis(n, 5, 1)]
+    X = Q[0] @ np.ones((5, 4)) + 1e-3 * gallery.tall_skinny(n, 4, seed=3)
+    info = {}
+    QZ, RZ = api.projectAndNormalize(Q, X, False, backend="tsqr", info=info)
+    QZo, RZo = kernels.projectAndNormalize(Q, X, False, backend="tsqr")
+    assert info["second_pass"] is False
+    assert rel(RZ[0], RZo[0]) < 1e-12 and rel(RZ[1], RZo[1]) < 1e-9
+
+
+def test_full_size_orth_properties():
+    # C5-like size-independent checks at n = 4e6: QR = X, Q'Q = I, R equal across backends
+    n, c = 4_000_000, 9
+    X = gallery.tall_skinny(n, c, seed=0)
+    Qt, Rt = api.tsqr(X)
+    Qc, Rc = api.cholqr(X)
+    assert rel(Rt, Rc) < 1e-9
+    assert orth(Qt) < 1e-13 and orth(Qc) < 1e-9
+    assert rel(Qt @ Rt, X) < 1e-13 and rel(Qc @ Rc, X) < 1e-13
