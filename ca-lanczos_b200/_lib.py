@@ -15,7 +15,7 @@ OK = 0
 ERR_CHOL = 4
 LAYOUT = {"auto": 0, "csr": 1, "sell": 2}
 LAYOUT_NAME = {v: k for k, v in LAYOUT.items()}
-QR = {"tsqr": 0, "cholqr": 1}
+QR = {"tsqr": 0, "cholqr": 1, "cholqr2": 2}
 
 c_i64 = C.c_int64
 c_dp = C.POINTER(C.c_double)

@@ -34,7 +34,7 @@ def set_qr_backend(name: str):
     """Select the QR used at the normalize.m:14 seam: 'tsqr' (reference default) or 'cholqr' (cholqr.m)."""
     global _QR_BACKEND
     if name not in _lib.QR:
-        raise ValueError("backend must be 'tsqr' or 'cholqr'")
+        raise ValueError("backend must be 'tsqr', 'cholqr' or 'cholqr2'")
     _QR_BACKEND = name
 
 

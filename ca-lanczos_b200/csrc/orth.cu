@@ -42,12 +42,49 @@ bool empty_block(const double* const* Qblk, const int* mcols, int i) { return !Q
 // decision (optional): norm-drop flag from the columns of R against nb2.
 int factor_r(calz_ctx* ctx, int backend, int64_t n, int c, const double* S, int64_t ldS, double* G_dev, double* R_dev,
              int* info_dev, const double* nb2, int nb2_stride, int* flag_dev, const int* pred, int want) {
-    if (backend == CALZ_QR_CHOLQR) {
+    if (backend == CALZ_QR_CHOLQR || backend == CALZ_QR_CHOLQR2) {
         CALZ_TRY(tsmm_tn(ctx, n, one_panel(S, ldS, c), S, ldS, c, G_dev, c, true, pred, want, true));
         return chol_small(ctx, c, G_dev, R_dev, info_dev, nb2, nb2_stride, flag_dev, pred, want);
     }
     CALZ_TRY(tsqr_factor(ctx, n, c, S, ldS, R_dev, pred, want));
     if (nb2) CALZ_TRY(norm_drop_decision(ctx, c, R_dev, nb2, nb2_stride, flag_dev));
+    return CALZ_OK;
+}
+
+// Q of a Cholesky-based QR: Rfin = (*sel ? R_b : R_a); Q = S / Rfin; with `adaptive` (CALZ_QR_CHOLQR2) a second
+// CholQR pass on Q runs on the device iff the conditioning estimate asks for it: G2 = Q'Q, Rb = chol(G2),
+// Q = Q / Rb, Rfin = Rb * Rfin.  G must be the Gram matrix the selected factor came from.
+// ints: [0] reorth flag, [1] chol info of the second pass.
+int cholqr_tail(calz_ctx* ctx, int64_t n, int c, const double* S, int64_t ldS, double* Q, int64_t ldQ, const double* R_a,
+                const double* R_b, const int* sel, const double* G, double* Rfin, double* G2, double* Rb, int* ints,
+                bool adaptive) {
+    CALZ_TRY(select_r(ctx, c, R_a, R_b, sel, G, Rfin, ints, adaptive));
+    CALZ_TRY(ts_trsolve(ctx, n, c, S, ldS, Rfin, Q, ldQ, nullptr, 0));
+    if (!adaptive) return CALZ_OK;
+    CALZ_TRY(tsmm_tn(ctx, n, one_panel(Q, ldQ, c), Q, ldQ, c, G2, c, true, ints, 1, true));
+    CALZ_TRY(chol_small(ctx, c, G2, Rb, ints + 1, nullptr, 0, nullptr, ints, 1));
+    CALZ_TRY(ts_trsolve(ctx, n, c, Q, ldQ, Rb, Q, ldQ, ints, 1));
+    return rmul_upper(ctx, c, Rb, Rfin, ints, 1);
+}
+
+// cholqr.m (single pass) or its CholQR2 variant: R on the host, info = failing pivot (0: none)
+int cholqr_device(calz_ctx* ctx, int64_t n, int c, const double* X, int64_t ldX, double* Q, int64_t ldQ, double* R,
+                  int* info, bool adaptive) {
+    const size_t cc = (size_t)c * c;
+    double* sm;
+    CALZ_TRY(small_scratch(ctx, 8 + 5 * cc, &sm));
+    int* flags = (int*)sm;                       // [0] info, [2] reorth, [3] info of the second pass
+    CALZ_CUDA(ctx, cudaMemsetAsync(sm, 0, 8 * sizeof(double), ctx->stream));
+    double *G = sm + 8, *R1 = G + cc, *Rfin = R1 + cc, *G2 = Rfin + cc, *Rb = G2 + cc;
+    CALZ_TRY(factor_r(ctx, CALZ_QR_CHOLQR, n, c, X, ldX, G, R1, flags, nullptr, 0, nullptr, nullptr, 0));
+    CALZ_TRY(cholqr_tail(ctx, n, c, X, ldX, Q, ldQ, R1, R1, nullptr, G, Rfin, G2, Rb, flags + 2, adaptive));
+    CALZ_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, sm, (8 + 5 * cc) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int* hf = (const int*)ctx->pinned;
+    const int inf = hf[0] ? hf[0] : (hf[2] ? hf[3] : 0);
+    memcpy(R, ctx->pinned + 8 + 2 * cc, cc * sizeof(double));
+    if (info) *info = inf;
+    if (inf) return set_error(ctx, CALZ_ERR_CHOL, "cholqr: Gram matrix not positive definite at pivot %d", inf);
     return CALZ_OK;
 }
 
@@ -64,19 +101,7 @@ int calz_gram(calz_ctx* ctx, int64_t n, int m, const double* A, int64_t ldA, int
 int calz_cholqr(calz_ctx* ctx, int64_t n, int c, const double* X, int64_t ldX, double* Q, int64_t ldQ, double* R, int* info) {
     if (!ctx || !X || !Q || !R || n < 1 || c < 1 || c > kMaxC) return set_error(ctx, CALZ_ERR_BADARG, "calz_cholqr: bad arguments");
     CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
-    double* sm;
-    CALZ_TRY(small_scratch(ctx, 2 + 2 * (size_t)c * c, &sm));
-    int* flags = (int*)sm;
-    double *G = sm + 2, *Rd = G + (size_t)c * c;
-    CALZ_TRY(factor_r(ctx, CALZ_QR_CHOLQR, n, c, X, ldX, G, Rd, flags, nullptr, 0, nullptr, nullptr, 0));
-    CALZ_TRY(ts_trsolve(ctx, n, c, X, ldX, Rd, Rd, nullptr, Q, ldQ));
-    CALZ_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, sm, (2 + 2 * (size_t)c * c) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const int inf = ((int*)ctx->pinned)[0];
-    memcpy(R, ctx->pinned + 2 + (size_t)c * c, (size_t)c * c * sizeof(double));
-    if (info) *info = inf;
-    if (inf) return set_error(ctx, CALZ_ERR_CHOL, "cholqr: Gram matrix not positive definite at pivot %d", inf);
-    return CALZ_OK;
+    return cholqr_device(ctx, n, c, X, ldX, Q, ldQ, R, info, false);      // cholqr.m:3-8 as written: one pass
 }
 
 int calz_tsqr(calz_ctx* ctx, int64_t n, int c, const double* A, int64_t ldA, double* Q, int64_t ldQ, double* R) {
@@ -96,9 +121,11 @@ int calz_normalize(calz_ctx* ctx, int64_t n, int c, const double* X, int64_t ldX
                    int64_t ldQ, double* R, int* rank) {
     if (tol <= 0) tol = 1.0e-8;      // normalize.m:8-10
     int st;
-    if (backend == CALZ_QR_CHOLQR) {
+    if (backend == CALZ_QR_CHOLQR || backend == CALZ_QR_CHOLQR2) {
+        if (!ctx || !X || !Q || !R || n < 1 || c < 1 || c > kMaxC) return set_error(ctx, CALZ_ERR_BADARG, "calz_normalize: bad arguments");
+        CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
         int info = 0;
-        st = calz_cholqr(ctx, n, c, X, ldX, Q, ldQ, R, &info);
+        st = cholqr_device(ctx, n, c, X, ldX, Q, ldQ, R, &info, backend == CALZ_QR_CHOLQR2);
     } else if (backend == CALZ_QR_TSQR) {
         st = calz_tsqr(ctx, n, c, X, ldX, Q, ldQ, R);
     } else {
@@ -164,7 +191,7 @@ int calz_project(calz_ctx* ctx, int64_t n, int nblk, const double* const* Qblk, 
 int calz_project_and_normalize(calz_ctx* ctx, int64_t n, int nblk, const double* const* Qblk, const int64_t* ldQ,
                                const int* mcols, int c, const double* X, int64_t ldX, int doreorth, int backend,
                                double* QZ, int64_t ldQZ, double* const* Rblk, double* Rlast, int* second_pass, int* rank) {
-    if (!ctx || !X || !QZ || n < 1 || c < 1 || c > kMaxC || nblk < 0 || (backend != CALZ_QR_TSQR && backend != CALZ_QR_CHOLQR))
+    if (!ctx || !X || !QZ || n < 1 || c < 1 || c > kMaxC || nblk < 0 || (backend != CALZ_QR_TSQR && backend != CALZ_QR_CHOLQR && backend != CALZ_QR_CHOLQR2))
         return set_error(ctx, CALZ_ERR_BADARG, "calz_project_and_normalize: bad arguments");
     if (QZ == X) return set_error(ctx, CALZ_ERR_BADARG, "calz_project_and_normalize: QZ must not alias X");
     CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -187,11 +214,14 @@ int calz_project_and_normalize(calz_ctx* ctx, int64_t n, int nblk, const double*
     const size_t offG = doubles; doubles += (size_t)c * c;
     const size_t offR1 = doubles; doubles += (size_t)c * c;
     const size_t offR2 = doubles; doubles += (size_t)c * c;
+    const size_t offRf = doubles; doubles += (size_t)c * c;       // R of the last normalize (what the host reads)
+    const size_t offG2 = doubles; doubles += (size_t)c * c;       // CholQR2 scratch
+    const size_t offRb = doubles; doubles += (size_t)c * c;
     double* sm;
     CALZ_TRY(small_scratch(ctx, doubles, &sm));
     int* flags = (int*)sm;
     CALZ_CUDA(ctx, cudaMemsetAsync(sm, 0, 8 * sizeof(double), ctx->stream));
-    double *G = sm + offG, *R1 = sm + offR1, *R2 = sm + offR2;
+    double *G = sm + offG, *R1 = sm + offR1, *R2 = sm + offR2, *Rf = sm + offRf;
 
     // ---- pass 1: Y = X - sum_i Q_i (Q_i' X)   (sequential over blocks, project.m:32-39); Y lives in QZ
     const double* src = X;
@@ -227,9 +257,12 @@ int calz_project_and_normalize(calz_ctx* ctx, int64_t n, int nblk, const double*
         CALZ_TRY(factor_r(ctx, backend, n, c, QZ, ldQZ, G, R2, flags + 2, nullptr, 0, nullptr, flags, 1));
     }
     // ---- Q of the LAST normalize only
-    if (backend == CALZ_QR_CHOLQR) {
-        CALZ_TRY(ts_trsolve(ctx, n, c, src, ldsrc, R1, R2, flags, QZ, ldQZ));
+    if (backend != CALZ_QR_TSQR) {
+        // G still holds the Gram matrix of whichever factorisation ran last (pass-2 kernels are skipped otherwise)
+        CALZ_TRY(cholqr_tail(ctx, n, c, src, ldsrc, QZ, ldQZ, R1, R2, flags, G, Rf, sm + offG2, sm + offRb, flags + 4,
+                             backend == CALZ_QR_CHOLQR2));
     } else {
+        CALZ_TRY(select_r(ctx, c, R1, R2, flags, G, Rf, nullptr, false));
         // the reflectors on the device belong to the last factorisation that actually ran (Y, or Z if pass 2 fired)
         CALZ_TRY(tsqr_form_q(ctx, n, c, src, ldsrc, QZ, ldQZ));
     }
@@ -240,7 +273,8 @@ int calz_project_and_normalize(calz_ctx* ctx, int64_t n, int nblk, const double*
     const double* h = ctx->pinned;
     const int* hf = (const int*)h;
     const bool second = hf[0] != 0;
-    const int info = second ? hf[2] : hf[1];
+    int info = second ? hf[2] : hf[1];
+    if (!info && hf[4]) info = hf[5];
     if (second_pass) *second_pass = second ? 1 : 0;
     for (int k = 0; k < nb; ++k) {
         const int i = blocks[k], m = mcols[i];
@@ -252,7 +286,7 @@ int calz_project_and_normalize(calz_ctx* ctx, int64_t n, int nblk, const double*
                 Rblk[i][(size_t)j * m + a] = v;
             }
     }
-    const double* Rl = h + (second ? offR2 : offR1);
+    const double* Rl = h + offRf;
     if (Rlast) memcpy(Rlast, Rl, (size_t)c * c * sizeof(double));
     if (rank) *rank = numerical_rank(c, Rl, c, 1.0e-8);
     if (info) return set_error(ctx, CALZ_ERR_CHOL, "projectAndNormalize/cholqr: Gram matrix not positive definite at pivot %d (pass %d)",

@@ -246,11 +246,11 @@ int ts_update(calz_ctx* ctx, int64_t n, const double* Q, int64_t ldQ, int M, con
 // One row per thread, forward substitution along the row: q_j = (x_j - sum_{i<j} q_i R_ij) / R_jj.
 template <int CT>
 __global__ void __launch_bounds__(kTsThreads, (CT == 1 ? 4 : (CT == 2 ? 3 : 2)))
-k_trsolve(long long n, int c, const double* X, long long ldX, const double* __restrict__ Ra,
-          const double* __restrict__ Rb, const int* __restrict__ sel, double* Q, long long ldQ) {
+k_trsolve(long long n, int c, const double* X, long long ldX, const double* __restrict__ R, double* Q, long long ldQ,
+          const int* __restrict__ pred, int want) {
+    if (pred && *pred != want) return;
     constexpr int CW = 8 * CT;
     __shared__ double Rs[CW][CW + 1];
-    const double* R = (sel && *sel) ? Rb : Ra;
     for (int e = threadIdx.x; e < CW * CW; e += kTsThreads) {
         const int i = e / CW, j = e % CW;
         Rs[i][j] = (i < c && j < c) ? R[(size_t)j * c + i] : (i == j ? 1.0 : 0.0);
@@ -277,14 +277,14 @@ k_trsolve(long long n, int c, const double* X, long long ldX, const double* __re
     }
 }
 
-int ts_trsolve(calz_ctx* ctx, int64_t n, int c, const double* X, int64_t ldX, const double* R_a, const double* R_b,
-               const int* sel, double* Q, int64_t ldQ) {
+int ts_trsolve(calz_ctx* ctx, int64_t n, int c, const double* X, int64_t ldX, const double* R, double* Q, int64_t ldQ,
+               const int* pred, int want) {
     if (n <= 0 || c <= 0) return CALZ_OK;
     if (c > kMaxC) return set_error(ctx, CALZ_ERR_UNSUPPORTED, "block width c=%d > %d", c, kMaxC);
     const int CT = (c + 7) / 8;
     int grid;
     grid = (int)((n + kTsThreads - 1) / kTsThreads);
-#define CALZ_TR(CTv) k_trsolve<CTv><<<grid, kTsThreads, 0, ctx->stream>>>(n, c, X, ldX, R_a, R_b, sel, Q, ldQ)
+#define CALZ_TR(CTv) k_trsolve<CTv><<<grid, kTsThreads, 0, ctx->stream>>>(n, c, X, ldX, R, Q, ldQ, pred, want)
     if (CT == 1) { CALZ_TR(1); } else if (CT == 2) { CALZ_TR(2); } else if (CT == 3) { CALZ_TR(3); } else { CALZ_TR(4); }
 #undef CALZ_TR
     CALZ_LAUNCH_CHECK(ctx);
@@ -360,6 +360,55 @@ __global__ void k_norm_drop(int c, const double* __restrict__ R, const double* _
 
 int norm_drop_decision(calz_ctx* ctx, int c, const double* R_dev, const double* nb2, int nb2_stride, int* flag_out) {
     k_norm_drop<<<1, 32, 0, ctx->stream>>>(c, R_dev, nb2, nb2_stride, flag_out);
+    CALZ_LAUNCH_CHECK(ctx);
+    return CALZ_OK;
+}
+
+__global__ void k_select_r(int c, const double* __restrict__ Ra, const double* __restrict__ Rb, const int* __restrict__ sel,
+                           const double* __restrict__ G, double* __restrict__ Rfin, int* reorth_out, int adaptive, double thresh) {
+    const double* R = (sel && *sel) ? Rb : Ra;
+    const int lane = threadIdx.x;
+    for (int e = lane; e < c * c; e += 32) Rfin[e] = R[e];
+    if (reorth_out) {
+        // sine of the angle between column j and the span of the previous ones; 1/min is a lower bound of the
+        // equilibrated condition number, which is what governs the accuracy of a Cholesky-based QR
+        double worst = 1.0;
+        if (adaptive && lane < c) {
+            const double gjj = G[(size_t)lane * c + lane];
+            worst = gjj > 0.0 ? R[(size_t)lane * c + lane] / sqrt(gjj) : 0.0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) worst = fmin(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+        if (lane == 0) *reorth_out = (adaptive && worst < thresh) ? 1 : 0;
+    }
+}
+
+int select_r(calz_ctx* ctx, int c, const double* R_a, const double* R_b, const int* sel, const double* G, double* Rfin,
+             int* reorth_out, bool adaptive) {
+    k_select_r<<<1, 32, 0, ctx->stream>>>(c, R_a, R_b, sel, G, Rfin, reorth_out, adaptive ? 1 : 0,
+                                          1.0 / (double)ctx->opt_cholqr2_inv_thresh);
+    CALZ_LAUNCH_CHECK(ctx);
+    return CALZ_OK;
+}
+
+__global__ void k_rmul_upper(int c, const double* __restrict__ Rb, double* Rfin, const int* __restrict__ pred, int want) {
+    if (pred && *pred != want) return;
+    __shared__ double A[kMaxC][kMaxC + 1], B[kMaxC][kMaxC + 1];
+    for (int e = threadIdx.x; e < c * c; e += blockDim.x) {
+        A[e % c][e / c] = Rb[e];
+        B[e % c][e / c] = Rfin[e];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < c * c; e += blockDim.x) {
+        const int i = e % c, j = e / c;
+        double s = 0.0;
+        for (int k = i; k <= j; ++k) s = fma(A[i][k], B[k][j], s);
+        Rfin[e] = (i <= j) ? s : 0.0;
+    }
+}
+
+int rmul_upper(calz_ctx* ctx, int c, const double* Rb, double* Rfin, const int* pred, int want) {
+    k_rmul_upper<<<1, 256, 0, ctx->stream>>>(c, Rb, Rfin, pred, want);
     CALZ_LAUNCH_CHECK(ctx);
     return CALZ_OK;
 }

@@ -33,9 +33,15 @@ int tsmm_tn(calz_ctx* ctx, int64_t n, const Panels& A, const double* B, int64_t 
 int ts_update(calz_ctx* ctx, int64_t n, const double* Q, int64_t ldQ, int M, const double* C_dev, int ldC,
               const double* X, int64_t ldX, int c, double* Y, int64_t ldY, const int* pred, int want);
 
-// Q = X / R  with R = *sel ? R_b : R_a (device c x c upper, ld c).  Q may alias X.
-int ts_trsolve(calz_ctx* ctx, int64_t n, int c, const double* X, int64_t ldX, const double* R_a,
-               const double* R_b, const int* sel, double* Q, int64_t ldQ);
+// Q = X / R  (R device c x c upper, ld c).  Q may alias X.
+int ts_trsolve(calz_ctx* ctx, int64_t n, int c, const double* X, int64_t ldX, const double* R, double* Q,
+               int64_t ldQ, const int* pred, int want);
+
+// Rfin = *sel ? R_b : R_a;  *reorth_out = adaptive && min_j Rfin_jj / sqrt(G_jj) < 1/inv_thresh
+int select_r(calz_ctx* ctx, int c, const double* R_a, const double* R_b, const int* sel, const double* G,
+             double* Rfin, int* reorth_out, bool adaptive);
+// Rfin = Rb * Rfin (upper triangular product), predicated
+int rmul_upper(calz_ctx* ctx, int c, const double* Rb, double* Rfin, const int* pred, int want);
 
 // R = chol(G) on the device (one warp), optional norm-drop decision of projectAndNormalize.m:45-52:
 // *flag_out = max_i |sqrt(nb2[i*nb2_stride]) - ||R(:,i)|| | / sqrt(nb2[...]) > 0.5.  info_out: 0 or failing pivot.

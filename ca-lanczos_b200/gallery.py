@@ -12,15 +12,19 @@ import numpy as np
 import scipy.sparse as sp
 
 
-def _stencil_csr(dims, diag):
+def _stencil_csr(dims, diag, row_lo=0, row_hi=None):
     """CSR of the (2*d+1)-point Dirichlet Laplacian stencil on a ``dims`` grid (first dim fastest).
 
-    Built directly in CSR (no COO/kron intermediate) so that 256^3 fits comfortably in host RAM.
+    Built directly in CSR (no COO/kron intermediate) so that 256^3 fits comfortably in host RAM.  With
+    ``row_lo/row_hi`` only rows [row_lo,row_hi) are generated (shape (row_hi-row_lo) x n, global columns):
+    what one rank of a row-partitioned run needs.
     """
     dims = tuple(int(d) for d in dims)
-    n = int(np.prod(dims))
+    ntot = int(np.prod(dims))
+    row_hi = ntot if row_hi is None else int(row_hi)
     strides = np.cumprod((1,) + dims[:-1]).astype(np.int64)
-    idx = np.arange(n, dtype=np.int64)
+    idx = np.arange(int(row_lo), row_hi, dtype=np.int64)
+    n = idx.shape[0]
     coords = [(idx // st) % d for st, d in zip(strides, dims)]
     # neighbour offsets in ascending column order: -s_d .. -s_1, 0, +s_1 .. +s_d
     offs, valid = [], []
@@ -37,7 +41,7 @@ def _stencil_csr(dims, diag):
     vals = np.where(np.asarray(offs) == 0, float(diag), -1.0)
     data = np.broadcast_to(vals[None, :], valid.shape)[valid].astype(np.float64)
     it = np.int32 if indptr[-1] < 2**31 else np.int64
-    A = sp.csr_matrix((data, cols.astype(np.int32), indptr.astype(it)), shape=(n, n))
+    A = sp.csr_matrix((data, cols.astype(np.int32), indptr.astype(it)), shape=(n, ntot))
     A.has_sorted_indices = True
     return A
 
@@ -47,11 +51,27 @@ def poisson2d(m: int) -> sp.csr_matrix:
     return _stencil_csr((m, m), 4.0)
 
 
-def laplace3d(m: int, my: int | None = None, mz: int | None = None) -> sp.csr_matrix:
-    """7-point Dirichlet Laplacian on an m x my x mz grid, x fastest; diag 6, off -1 (C3: m=256)."""
+def laplace3d(m: int, my: int | None = None, mz: int | None = None, row_lo: int = 0,
+              row_hi: int | None = None) -> sp.csr_matrix:
+    """7-point Dirichlet Laplacian on an m x my x mz grid, x fastest; diag 6, off -1 (C3: m=256).
+    ``row_lo/row_hi``: generate only that row range (rectangular result, global column indices)."""
     my = m if my is None else my
     mz = m if mz is None else mz
-    return _stencil_csr((m, my, mz), 6.0)
+    return _stencil_csr((m, my, mz), 6.0, row_lo, row_hi)
+
+
+def leja_points(a: float, b: float, s: int) -> np.ndarray:
+    """s Chebyshev points of [a,b] in Leja order (max-product greedy): the textbook Newton-basis shifts when
+    the spectral interval is known (bench.py uses them for the 7-point Laplacian, spectrum in (0,12))."""
+    k = np.arange(s)
+    x = 0.5 * (a + b) + 0.5 * (b - a) * np.cos((2 * k + 1) * np.pi / (2 * s))
+    out = [int(np.argmax(np.abs(x)))]
+    rest = [i for i in range(s) if i != out[0]]
+    while rest:
+        prod = [np.prod(np.abs(x[i] - x[out])) for i in rest]
+        j = rest[int(np.argmax(prod))]
+        out.append(j); rest.remove(j)
+    return x[out]
 
 
 def diag_linspace(n: int, K: float = 100.0) -> sp.csr_matrix:

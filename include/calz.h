@@ -44,7 +44,10 @@ extern "C" {
 
 /* QR backend at the normalize.m:14 seam */
 #define CALZ_QR_TSQR            0   /* tsqr.m:7-12   (reference default) */
-#define CALZ_QR_CHOLQR          1   /* cholqr.m:3-8 */
+#define CALZ_QR_CHOLQR          1   /* cholqr.m:3-8, single pass (orthogonality ~ kappa^2 eps) */
+#define CALZ_QR_CHOLQR2         2   /* cholqr.m + an automatic second CholQR pass (R = R2*R1) when the on-device
+                                       conditioning estimate min_j R_jj/||x_j|| says one pass is not
+                                       Householder-accurate; identical kernels and results to CHOLQR otherwise */
 
 typedef struct calz_ctx calz_ctx;   /* one per process / per GPU: device, stream, scratch, communicator */
 typedef struct calz_mat calz_mat;   /* device sparse matrix: owned rows + level-s ghost closure */
@@ -59,7 +62,8 @@ void* calz_get_stream(calz_ctx* ctx);
 int  calz_sync(calz_ctx* ctx);
 /* number of kernels launched by this library since the last reset (bench.py "gpu_launches") */
 int64_t calz_launch_count(calz_ctx* ctx, int reset);
-/* knobs: "mpk_l2_chunk_bytes" (0 = no temporal blocking), "sell_sigma", "csr_lanes", "grid_mult" */
+/* knobs: "mpk_l2_chunk_bytes" (0 = no temporal blocking), "sell_sigma", "csr_lanes", "grid_mult",
+ * "cholqr2_inv_thresh" (second pass when min_j R_jj/||x_j|| < 1/value; default 32) */
 int  calz_set_option(calz_ctx* ctx, const char* key, int64_t value);
 
 /* ------------------------------------------------------------------ multi-GPU plumbing --------------- */

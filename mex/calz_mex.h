@@ -56,7 +56,9 @@ inline calz_ctx* calz_mex_context() {
 // normalize.m:14 seam: tsqr (reference default) unless CALZ_QR_BACKEND=cholqr
 inline int calz_mex_backend() {
     const char* b = getenv("CALZ_QR_BACKEND");
-    return (b && !strcmp(b, "cholqr")) ? CALZ_QR_CHOLQR : CALZ_QR_TSQR;
+    if (b && !strcmp(b, "cholqr")) return CALZ_QR_CHOLQR;
+    if (b && !strcmp(b, "cholqr2")) return CALZ_QR_CHOLQR2;
+    return CALZ_QR_TSQR;
 }
 
 // Device copy of a MATLAB sparse matrix, uploaded once and reused across calls (SURVEY.md §7 "hard parts").

@@ -86,6 +86,21 @@ def cholqr(X):
     return np.asfortranarray(Q), np.asfortranarray(R)
 
 
+def cholqr2(X, inv_thresh=32.0):
+    """NOT in the reference: cholqr.m followed by an automatic second CholQR pass (R = R2*R1) when
+    min_j R_jj/||x_j|| < 1/inv_thresh -- the restatement of libcalz' CALZ_QR_CHOLQR2 backend, kept here so the tests
+    can check that the device takes the same branch.  Its results are compared against tsqr (Householder)."""
+    X = np.asarray(X)
+    G = X.T @ X
+    R1 = np.linalg.cholesky(G).T
+    Q = sla.solve_triangular(R1, X.T, trans="T", lower=False).T
+    if np.min(np.diag(R1) / np.sqrt(np.diag(G))) < 1.0 / inv_thresh:
+        R2 = np.linalg.cholesky(Q.T @ Q).T
+        Q = sla.solve_triangular(R2, Q.T, trans="T", lower=False).T
+        R1 = R2 @ R1
+    return np.asfortranarray(Q), np.asfortranarray(R1)
+
+
 def normalize(X, opt="None", tol=1.0e-8, backend="tsqr"):
     """normalize.m:3-36 -- QR (tsqr.m:7 at the :14 seam; ``backend='cholqr'`` selects cholqr.m there),
     ``svd(R)``, numerical rank = #{sigma_i > tol*sigma_1} counted up to the first failure (:17-24).
@@ -94,7 +109,7 @@ def normalize(X, opt="None", tol=1.0e-8, backend="tsqr"):
     and is not restated.
     """
     ncols = X.shape[1]
-    Q, R = (tsqr if backend == "tsqr" else cholqr)(X)
+    Q, R = {"tsqr": tsqr, "cholqr": cholqr, "cholqr2": cholqr2}[backend](X)
     S = np.linalg.svd(R, compute_uv=False)
     abs_tol = tol * S[0]
     rank = ncols

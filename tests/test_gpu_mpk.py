@@ -148,4 +148,5 @@ def test_full_size_c2_basis_identity():
     B = np.zeros((s + 1, s)); B[np.arange(s), np.arange(s)] = lam; B[np.arange(1, s + 1), np.arange(s)] = 1
     assert np.linalg.norm(A @ V[:, :s] - V @ B) <= 1e-13 * np.linalg.norm(V)
     d = np.linspace(1, 100, n)                                    # diagonal A: closed form prod(d - lam_i) * v
-    np.testing.assert_allclose(V[:, s], np.prod(d[:, None] - lam[None, :], axis=1) * v, rtol=1e-12, atol=1e-3 * 1e-12)
+    exact = np.prod(d[:, None] - lam[None, :], axis=1) * v        # rows with d ~ lam_i cancel: compare norm-wise
+    assert np.linalg.norm(V[:, s] - exact) <= 1e-12 * np.linalg.norm(exact)

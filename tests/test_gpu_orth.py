@@ -48,7 +48,10 @@ def test_tsqr_zero_column_sign_zero():
     Q, R = api.tsqr(X)
     Qo, Ro = kernels.tsqr(X)
     assert R[1, 1] == 0.0 and np.all(Q[:, 1] == 0.0)              # sign(0) = 0 (tsqr.m:9)
-    assert rel(R, Ro) < 1e-13
+    assert np.all(R[1, :] == 0.0) and np.all(Ro[1, :] == 0.0)     # ... which also wipes row 2 of R, as in the reference
+    assert rel(R[0], Ro[0]) < 1e-13
+    # rank-deficient QR is not unique: the tree and LAPACK split column 3 differently between rows 2 and 3
+    assert abs(np.linalg.norm(R[:, 2]) - np.linalg.norm(X[:, 2])) < 1e-5 * np.linalg.norm(X[:, 2])
 
 
 @pytest.mark.parametrize("n,c", SHAPES)
@@ -67,9 +70,31 @@ def test_cholqr(n, c):
 
 
 def test_cholqr_not_positive_definite_raises():
-    X = np.ones((1000, 3), order="F")
+    X = gallery.tall_skinny(1000, 3, seed=1); X[:, 1] = 0.0       # exact zero pivot => chol fails (cholqr.m:6)
     with pytest.raises(np.linalg.LinAlgError):
         api.cholqr(X)
+    with pytest.raises(np.linalg.LinAlgError):
+        api.projectAndNormalize([], X, True, backend="cholqr")
+
+
+@pytest.mark.parametrize("n,c,scale", [(20000, 8, 1.0), (20000, 8, 1e-5), (50000, 9, 3e-7), (3000, 17, 1e-6)])
+def test_cholqr2_is_householder_accurate(n, c, scale):
+    # ill-conditioned block: X = [x1, x1 + scale*noise, ...]: kappa_eq ~ 1/scale.  One CholQR pass loses kappa^2*eps of
+    # orthogonality; the CHOLQR2 backend detects it on the device and re-orthogonalises, matching Householder.
+    B = gallery.tall_skinny(n, c, seed=c)
+    X = np.asfortranarray(B[:, [0]] + scale * B) if scale < 1 else B
+    Q2, R2, _ = api.normalize(X, backend="cholqr2")
+    Qo, Ro = kernels.tsqr(X)
+    Qr, Rr = kernels.cholqr2(X)
+    keq = np.linalg.cond(X / np.linalg.norm(X, axis=0))
+    assert orth(Q2) < 1e-13 * c
+    assert rel(Q2 @ R2, X) < 1e-14 * c
+    assert rel(R2, Ro) < max(1e-13, 100 * keq * EPS)
+    assert rel(R2, Rr) < max(1e-13, 100 * keq * EPS)
+    if scale == 1.0:                                              # well conditioned: the second pass must NOT run
+        Q1, R1 = api.cholqr(X)
+        np.testing.assert_array_equal(R1, R2)
+        np.testing.assert_array_equal(Q1, Q2)
 
 
 @pytest.mark.parametrize("backend", ["tsqr", "cholqr"])
@@ -122,7 +147,7 @@ def test_project_doreorth_branch():
         assert np.linalg.norm(Y - Yo) <= 1e-12 * np.linalg.norm(Xi)
 
 
-@pytest.mark.parametrize("backend", ["cholqr", "tsqr"])
+@pytest.mark.parametrize("backend", ["cholqr", "tsqr", "cholqr2"])
 @pytest.mark.parametrize("n,ms,c", [(6000, [5], 4), (50000, [9], 8), (4000, [9, 12], 8), (3000, [], 5), (3000, [0], 5), (7000, [17], 16)])
 def test_project_and_normalize(backend, n, ms, c):
     Q = []
@@ -143,7 +168,7 @@ def test_project_and_normalize(backend, n, ms, c):
         assert info["rank"] == info_o["rank"]
         assert len(RZ) == len(Q) + 1
         kappa = np.linalg.cond(RZo[-1])
-        tolR = 1e-10 if backend == "tsqr" else max(1e-10, 100 * kappa ** 2 * EPS)
+        tolR = 1e-10 if backend != "cholqr" else max(1e-10, 100 * kappa ** 2 * EPS)
         for r, ro in zip(RZ, RZo):
             assert (r is None) == (ro is None)
             if r is not None:
