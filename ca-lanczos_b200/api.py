@@ -225,8 +225,18 @@ def matrix_powers_monomial(A, q, s):
     return V
 
 
-def matrix_powers_newton(A, v, s, lam, modifiedp=0):
-    """matrix_powers_newton.m:15-54 -- V(:,1)=v; V(:,k+1)=A*V(:,k)-lam(k)*V(:,k); n x (s+1) (v included)."""
+def _out_array(out, shape):
+    """Optional caller-provided result buffer (e.g. pinned host memory); must be fp64, column-major, right shape."""
+    if out is None:
+        return np.empty(shape, order="F")
+    if out.shape != shape or out.dtype != np.float64 or not out.flags.f_contiguous:
+        raise ValueError("out must be a float64 Fortran-ordered array of shape %s" % (shape,))
+    return out
+
+
+def matrix_powers_newton(A, v, s, lam, modifiedp=0, out=None):
+    """matrix_powers_newton.m:15-54 -- V(:,1)=v; V(:,k+1)=A*V(:,k)-lam(k)*V(:,k); n x (s+1) (v included).
+    ``out`` (extension): write the result into a caller-owned array instead of a fresh one."""
     s = int(s)
     dm = _device_matrix(A, s)
     v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).ravel())
@@ -237,7 +247,7 @@ def matrix_powers_newton(A, v, s, lam, modifiedp=0):
         raise ValueError("matrix_powers_newton: need at least s shifts")
     re = np.ascontiguousarray(np.real(lam[:s]), dtype=np.float64)
     im = np.ascontiguousarray(np.imag(lam[:s]), dtype=np.float64) if np.iscomplexobj(lam) else None
-    V = np.empty((dm.n, s + 1), order="F")
+    V = _out_array(out, (dm.n, s + 1))
     try:
         check(dm.ctx.lib.calz_mpk_newton_host(dm.h, _dp(v), s, _dp(re), _dp(im) if im is not None else None,
                                               int(modifiedp), _dp(V), dm.n), dm.ctx.h)
@@ -329,7 +339,7 @@ def project(Q, X, doreorth=False, ctx: Context | None = None):
 
 
 def projectAndNormalize(Q, X, doreorth=True, backend: str | None = None, info: dict | None = None,
-                        ctx: Context | None = None):
+                        ctx: Context | None = None, out=None):
     """projectAndNormalize.m:3-90 -- returns (QZ, RZ) with RZ a list of len(Q)+1 blocks (last = R of the last
     normalize).  ``info`` receives 'second_pass' (the reference prints 'second', :62) and 'rank'."""
     ctx = ctx or default_context()
@@ -339,7 +349,7 @@ def projectAndNormalize(Q, X, doreorth=True, backend: str | None = None, info: d
     R = [np.zeros((mc[i], c), order="F") if (i < nb and mc[i] > 0) else None for i in range(nb)]
     rp = (_lib.c_dp * max(nb, 1))(*[(_dp(r) if r is not None else None) for r in R]) if nb else (_lib.c_dp * 1)()
     Rlast = np.zeros((c, c), order="F")
-    QZ = np.empty((n, c), order="F")
+    QZ = _out_array(out, (n, c))
     second = C.c_int(0); rank = C.c_int(0)
     st = ctx.lib.calz_project_and_normalize_host(ctx.h, n, nb, ptrs, lds, mc, c, _dp(X), n, 1 if doreorth else 0,
                                                  _lib.QR[backend or _QR_BACKEND], _dp(QZ), n, rp, _dp(Rlast),

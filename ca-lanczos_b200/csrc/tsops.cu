@@ -122,7 +122,17 @@ k_tsmm_tn(long long n, Panels A, int a0, const double* __restrict__ B, long long
         const int a = a0 + 8 * mt + i, b = b0 + 8 * ct + j;
         if (a >= M || b >= c) continue;
         double s = 0.0;
-        for (unsigned int blk = lane; blk < gridDim.x; blk += 32) s += __ldcg(partials + (size_t)blk * TILE_ELEMS + e);
+        // 8 independent L2 loads in flight per lane (a dependent one-by-one loop costs ~20 L2 latencies)
+        for (unsigned int blk0 = lane; blk0 < gridDim.x; blk0 += 256) {
+            double p[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const unsigned int blk = blk0 + 32 * q;
+                p[q] = blk < gridDim.x ? __ldcg(partials + (size_t)blk * TILE_ELEMS + e) : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) s += p[q];
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) C[(size_t)b * ldC + a] = s;
@@ -132,10 +142,10 @@ k_tsmm_tn(long long n, Panels A, int a0, const double* __restrict__ B, long long
 
 // persistent grid: one wave of CTAs, as many as are co-resident (occupancy API), capped by the work
 template <class K>
-static int resident_grid(calz_ctx* ctx, K kernel, long long work_items) {
+static int resident_grid(calz_ctx* ctx, K kernel, long long work_items, int cap = 1 << 20) {
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTsThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-    per_sm = (int)std::min<long long>(per_sm, ctx->opt_grid_mult);
+    per_sm = (int)std::min<long long>(std::min(per_sm, cap), ctx->opt_grid_mult);
     long long grid = std::min<long long>((long long)ctx->num_sms * per_sm, work_items);
     return (int)std::max<long long>(grid, 1);
 }
@@ -145,7 +155,7 @@ static int launch_tsmm(calz_ctx* ctx, long long n, const Panels& A, int a0, cons
                        int M, int c, double* C, int ldC, bool same, const int* pred, int want) {
     const bool sm = same && MT == CT;
     const int grid = sm ? resident_grid(ctx, k_tsmm_tn<MT, CT, true>, (n + 127) / 128)
-                        : resident_grid(ctx, k_tsmm_tn<MT, CT, false>, (n + 127) / 128);
+                        : resident_grid(ctx, k_tsmm_tn<MT, CT, false>, (n + 127) / 128, 2);   // measured: 2 CTAs/SM beat 4-8 here
     CALZ_TRY(reserve(ctx, ctx->partials, (size_t)grid * MT * CT * 64 * sizeof(double)));
     double* part = (double*)ctx->partials.p;
     if (sm)

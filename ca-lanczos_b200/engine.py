@@ -96,13 +96,19 @@ class BlockEngine:
         return Rk.copy()
 
     # ---- ca_lanczos.m:184-223 ('local')
-    def next_block(self, assemble_T: bool = True):
+    def next_block(self, assemble_T: bool = True, events=None):
+        """``events``: optional ((e0,e1,e2), stream) -- torch CUDA events recorded on libcalz' stream before the MPK,
+        between MPK and projectAndNormalize, and after it (bench.py's per-phase timing)."""
         s = self.s
         self.k += 1
         k = self.k
         if k * s + 1 > self.max_cols:
             raise RuntimeError("BlockEngine: Q storage exhausted")
+        if events is not None:
+            events[0][0].record(events[1])
         V, ldV = self._mpk(self._qcol((k - 1) * s))
+        if events is not None:
+            events[0][1].record(events[1])
         qblk = (C.c_void_p * 1)(self._qcol((k - 2) * s))
         lds = (C.c_int64 * 1)(self.ld)
         mc = (C.c_int * 1)(s + 1)
@@ -112,6 +118,8 @@ class BlockEngine:
                                                   1, _lib.QR[self.backend], C.c_void_p(self._qcol((k - 1) * s + 1)),
                                                   self.ld, rp, self._Rl.ctypes.data_as(_lib.c_dp), C.byref(second),
                                                   C.byref(rank)), self.ctx.h)
+        if events is not None:
+            events[0][2].record(events[1])
         self.second.append(bool(second.value))
         if assemble_T:
             self._extend_T(k, self._R1, self._Rl)

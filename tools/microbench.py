@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--layouts", default="sell,csr")
     ap.add_argument("--chunks", default="0")
     ap.add_argument("--skip-orth", action="store_true")
+    ap.add_argument("--skip-mpk", action="store_true")
+    ap.add_argument("--ldpad", type=int, default=0)
     args = ap.parse_args()
     m, s = args.m, args.s
     ctx = api.default_context()
@@ -58,7 +60,7 @@ def main():
     v = torch.full((n,), 1.0 / np.sqrt(n), dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
     out = {}
-    for layout in args.layouts.split(","):
+    for layout in ([] if args.skip_mpk else args.layouts.split(",")):
         t0 = time.time()
         dm = api.DeviceMatrix(A, s_max=s, layout=layout)
         print("layout %s: upload %.1fs sell_padded=%d lanes=%d" % (layout, time.time() - t0, dm.info("sell_padded_nnz"), dm.info("csr_lanes")), flush=True)
@@ -78,7 +80,8 @@ def main():
     if args.skip_orth:
         return
     # ---- orthogonalisation kernels on n x c blocks
-    ld = (n + 31) // 32 * 32
+    ld = (n + 31) // 32 * 32 + args.ldpad
+    print("orth blocks: n=%d ld=%d (pad %d)" % (n, ld, args.ldpad))
     Q = torch.randn((s + 1, ld), dtype=torch.float64, device=dev)
     X = torch.randn((s, ld), dtype=torch.float64, device=dev)
     Y = torch.empty((s + 1, ld), dtype=torch.float64, device=dev)
@@ -103,7 +106,7 @@ def main():
     # full projectAndNormalize with a block that triggers pass 2: X = Q*ones + small
     Qo = torch.linalg.qr(Q[:, :n].T.contiguous())[0]            # n x (s+1) orthonormal (torch, setup only)
     Q[:, :n] = Qo.T
-    X[:, :n] = (Qo @ torch.ones((s + 1, s), dtype=torch.float64, device=dev) + 1e-3 * torch.randn((n, s), dtype=torch.float64, device=dev)).T
+    X[:, :n] = (Qo @ torch.ones((s + 1, s), dtype=torch.float64, device=dev) + (1e-3 / np.sqrt(n)) * torch.randn((n, s), dtype=torch.float64, device=dev)).T
     del Qo
     torch.cuda.synchronize()
     qblk = (C.c_void_p * 1)(Q.data_ptr()); lds = (C.c_int64 * 1)(ld); mc = (C.c_int * 1)(s + 1)
