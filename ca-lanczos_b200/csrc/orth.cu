@@ -39,32 +39,40 @@ int small_scratch(calz_ctx* ctx, size_t doubles, double** p) {
 bool empty_block(const double* const* Qblk, const int* mcols, int i) { return !Qblk || !Qblk[i] || !mcols || mcols[i] <= 0; }
 
 // QR of S (n x c) by `backend`: R -> R_dev; with CholQR the Gram matrix goes through G_dev.
-// decision (optional): norm-drop flag from the columns of R against nb2.
+// decision (optional): norm-drop flag from the columns of R against nb2.  cond_dev (CholQR2): "needs another pass".
 int factor_r(calz_ctx* ctx, int backend, int64_t n, int c, const double* S, int64_t ldS, double* G_dev, double* R_dev,
-             int* info_dev, const double* nb2, int nb2_stride, int* flag_dev, const int* pred, int want) {
+             int* info_dev, const double* nb2, int nb2_stride, int* flag_dev, const int* pred, int want, int* cond_dev = nullptr) {
     if (backend == CALZ_QR_CHOLQR || backend == CALZ_QR_CHOLQR2) {
         CALZ_TRY(tsmm_tn(ctx, n, one_panel(S, ldS, c), S, ldS, c, G_dev, c, true, pred, want, true));
-        return chol_small(ctx, c, G_dev, R_dev, info_dev, nb2, nb2_stride, flag_dev, pred, want);
+        return chol_small(ctx, c, G_dev, R_dev, info_dev, nb2, nb2_stride, flag_dev, pred, want, backend == CALZ_QR_CHOLQR2,
+                          backend == CALZ_QR_CHOLQR2 ? cond_dev : nullptr);
     }
     CALZ_TRY(tsqr_factor(ctx, n, c, S, ldS, R_dev, pred, want));
     if (nb2) CALZ_TRY(norm_drop_decision(ctx, c, R_dev, nb2, nb2_stride, flag_dev));
     return CALZ_OK;
 }
 
-// Q of a Cholesky-based QR: Rfin = (*sel ? R_b : R_a); Q = S / Rfin; with `adaptive` (CALZ_QR_CHOLQR2) a second
-// CholQR pass on Q runs on the device iff the conditioning estimate asks for it: G2 = Q'Q, Rb = chol(G2),
-// Q = Q / Rb, Rfin = Rb * Rfin.  G must be the Gram matrix the selected factor came from.
-// ints: [0] reorth flag, [1] chol info of the second pass.
-int cholqr_tail(calz_ctx* ctx, int64_t n, int c, const double* S, int64_t ldS, double* Q, int64_t ldQ, const double* R_a,
-                const double* R_b, const int* sel, const double* G, double* Rfin, double* G2, double* Rb, int* ints,
-                bool adaptive) {
-    CALZ_TRY(select_r(ctx, c, R_a, R_b, sel, G, Rfin, ints, adaptive));
-    CALZ_TRY(ts_trsolve(ctx, n, c, S, ldS, Rfin, Q, ldQ, nullptr, 0));
-    if (!adaptive) return CALZ_OK;
-    CALZ_TRY(tsmm_tn(ctx, n, one_panel(Q, ldQ, c), Q, ldQ, c, G2, c, true, ints, 1, true));
-    CALZ_TRY(chol_small(ctx, c, G2, Rb, ints + 1, nullptr, 0, nullptr, ints, 1));
-    CALZ_TRY(ts_trsolve(ctx, n, c, Q, ldQ, Rb, Q, ldQ, ints, 1));
-    return rmul_upper(ctx, c, Rb, Rfin, ints, 1);
+// CholQR2 refinement, driven from the host AFTER the small results came back (so the steady state, where the
+// conditioning estimate is fine, pays nothing): repeat { G = Q'Q; Rb = chol(G); Q = Q/Rb; Rfin = Rb*Rfin } while the
+// estimate still asks for it (at most 3 passes: a shifted first pass needs two more, "shifted CholeskyQR3").
+// scratch: 2*c*c doubles + 2 ints on the device.  Rfin_dev is updated in place; returns the last chol info.
+int cholqr_refine(calz_ctx* ctx, int64_t n, int c, double* Q, int64_t ldQ, double* Rfin_dev, double* scratch, int* ints_dev,
+                  int* info_out) {
+    const size_t cc = (size_t)c * c;
+    double *G2 = scratch, *Rb = scratch + cc;
+    *info_out = 0;
+    for (int pass = 0; pass < 3; ++pass) {
+        CALZ_TRY(tsmm_tn(ctx, n, one_panel(Q, ldQ, c), Q, ldQ, c, G2, c, true, nullptr, 0, true));
+        CALZ_TRY(chol_small(ctx, c, G2, Rb, ints_dev, nullptr, 0, nullptr, nullptr, 0, true, ints_dev + 1));
+        CALZ_TRY(ts_trsolve(ctx, n, c, Q, ldQ, Rb, Q, ldQ, nullptr, 0));
+        CALZ_TRY(rmul_upper(ctx, c, Rb, Rfin_dev, nullptr, 0));
+        int h[2];
+        CALZ_CUDA(ctx, cudaMemcpyAsync(h, ints_dev, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (h[0] > 0) { *info_out = h[0]; break; }
+        if (!h[1]) break;
+    }
+    return CALZ_OK;
 }
 
 // cholqr.m (single pass) or its CholQR2 variant: R on the host, info = failing pivot (0: none)
@@ -73,16 +81,22 @@ int cholqr_device(calz_ctx* ctx, int64_t n, int c, const double* X, int64_t ldX,
     const size_t cc = (size_t)c * c;
     double* sm;
     CALZ_TRY(small_scratch(ctx, 8 + 5 * cc, &sm));
-    int* flags = (int*)sm;                       // [0] info, [2] reorth, [3] info of the second pass
+    int* flags = (int*)sm;                       // [0] info, [1] cond, [2..3] refinement scratch
     CALZ_CUDA(ctx, cudaMemsetAsync(sm, 0, 8 * sizeof(double), ctx->stream));
-    double *G = sm + 8, *R1 = G + cc, *Rfin = R1 + cc, *G2 = Rfin + cc, *Rb = G2 + cc;
-    CALZ_TRY(factor_r(ctx, CALZ_QR_CHOLQR, n, c, X, ldX, G, R1, flags, nullptr, 0, nullptr, nullptr, 0));
-    CALZ_TRY(cholqr_tail(ctx, n, c, X, ldX, Q, ldQ, R1, R1, nullptr, G, Rfin, G2, Rb, flags + 2, adaptive));
-    CALZ_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, sm, (8 + 5 * cc) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    double *G = sm + 8, *R1 = G + cc, *scr = R1 + cc;
+    CALZ_TRY(factor_r(ctx, adaptive ? CALZ_QR_CHOLQR2 : CALZ_QR_CHOLQR, n, c, X, ldX, G, R1, flags, nullptr, 0, nullptr, nullptr, 0,
+                      flags + 1));
+    CALZ_TRY(ts_trsolve(ctx, n, c, X, ldX, R1, Q, ldQ, nullptr, 0));
+    CALZ_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, sm, (8 + 2 * cc) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const int* hf = (const int*)ctx->pinned;
-    const int inf = hf[0] ? hf[0] : (hf[2] ? hf[3] : 0);
-    memcpy(R, ctx->pinned + 8 + 2 * cc, cc * sizeof(double));
+    int inf = hf[0] > 0 ? hf[0] : 0;
+    if (!inf && adaptive && hf[1]) {
+        CALZ_TRY(cholqr_refine(ctx, n, c, Q, ldQ, R1, scr, flags + 2, &inf));
+        CALZ_CUDA(ctx, cudaMemcpyAsync(ctx->pinned + 8 + cc, R1, cc * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    memcpy(R, ctx->pinned + 8 + cc, cc * sizeof(double));
     if (info) *info = inf;
     if (inf) return set_error(ctx, CALZ_ERR_CHOL, "cholqr: Gram matrix not positive definite at pivot %d", inf);
     return CALZ_OK;
@@ -244,7 +258,8 @@ int calz_project_and_normalize(calz_ctx* ctx, int64_t n, int nblk, const double*
         nb2_stride = ld1[0] + 1;
     }
     // ---- normalize(Y): R1 (+ the norm-drop decision on the device)
-    CALZ_TRY(factor_r(ctx, backend, n, c, src, ldsrc, G, R1, flags + 1, nb2, nb2_stride, flags + 0, nullptr, 0));
+    // flags: [0] second pass, [1]/[2] chol info pass 1/2, [3]/[4] conditioning flag pass 1/2, [5] selected, [6..7] refinement
+    CALZ_TRY(factor_r(ctx, backend, n, c, src, ldsrc, G, R1, flags + 1, nb2, nb2_stride, flags + 0, nullptr, 0, flags + 3));
 
     // ---- pass 2, predicated on flags[0] == 1 (projectAndNormalize.m:61-73): Z = Y - sum_i Q_i (Q_i' Y), in place
     if (fuse_norms) {
@@ -254,15 +269,14 @@ int calz_project_and_normalize(calz_ctx* ctx, int64_t n, int nblk, const double*
             CALZ_TRY(tsmm_tn(ctx, n, one_panel(Qblk[i], ldQ[i], m), QZ, ldQZ, c, C, m, false, flags, 1, true));
             CALZ_TRY(ts_update(ctx, n, Qblk[i], ldQ[i], m, C, m, QZ, ldQZ, c, QZ, ldQZ, flags, 1));
         }
-        CALZ_TRY(factor_r(ctx, backend, n, c, QZ, ldQZ, G, R2, flags + 2, nullptr, 0, nullptr, flags, 1));
+        CALZ_TRY(factor_r(ctx, backend, n, c, QZ, ldQZ, G, R2, flags + 2, nullptr, 0, nullptr, flags, 1, flags + 4));
     }
     // ---- Q of the LAST normalize only
     if (backend != CALZ_QR_TSQR) {
-        // G still holds the Gram matrix of whichever factorisation ran last (pass-2 kernels are skipped otherwise)
-        CALZ_TRY(cholqr_tail(ctx, n, c, src, ldsrc, QZ, ldQZ, R1, R2, flags, G, Rf, sm + offG2, sm + offRb, flags + 4,
-                             backend == CALZ_QR_CHOLQR2));
+        CALZ_TRY(select_r(ctx, c, R1, R2, flags, flags + 3, flags + 4, Rf, flags + 5));
+        CALZ_TRY(ts_trsolve(ctx, n, c, src, ldsrc, Rf, QZ, ldQZ, nullptr, 0));
     } else {
-        CALZ_TRY(select_r(ctx, c, R1, R2, flags, G, Rf, nullptr, false));
+        CALZ_TRY(select_r(ctx, c, R1, R2, flags, nullptr, nullptr, Rf, nullptr));
         // the reflectors on the device belong to the last factorisation that actually ran (Y, or Z if pass 2 fired)
         CALZ_TRY(tsqr_form_q(ctx, n, c, src, ldsrc, QZ, ldQZ));
     }
@@ -274,7 +288,13 @@ int calz_project_and_normalize(calz_ctx* ctx, int64_t n, int nblk, const double*
     const int* hf = (const int*)h;
     const bool second = hf[0] != 0;
     int info = second ? hf[2] : hf[1];
-    if (!info && hf[4]) info = hf[5];
+    if (info < 0) info = 0;                                              // negative = shifted retries (CholQR2), not a failure
+    if (!info && backend == CALZ_QR_CHOLQR2 && hf[5]) {
+        // rare path: the conditioning estimate asks for re-orthogonalisation (first block of an ill-conditioned start)
+        CALZ_TRY(cholqr_refine(ctx, n, c, QZ, ldQZ, Rf, sm + offG2, flags + 6, &info));
+        CALZ_CUDA(ctx, cudaMemcpyAsync(ctx->pinned + offRf, Rf, (size_t)c * c * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     if (second_pass) *second_pass = second ? 1 : 0;
     for (int k = 0; k < nb; ++k) {
         const int i = blocks[k], m = mcols[i];

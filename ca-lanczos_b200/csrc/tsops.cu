@@ -317,35 +317,55 @@ __device__ void norm_drop_flag(int c, const double (*R)[kMaxC + 1], const double
     if (lane == 0) *flag_out = worst > 0.5 ? 1 : 0;
 }
 
+// One warp.  adaptive != 0 (CALZ_QR_CHOLQR2): a failed pivot restarts the factorisation of G + shift*I (shifted CholQR,
+// shift = 100*c*eps*max(diag G), x100 per retry) instead of giving up; *info_out = -(#shifts) then.  cond_out (optional):
+// 1 if a shift was needed or min_j R_jj/sqrt(G_jj) < thresh, i.e. one CholQR pass is not Householder-accurate.
 __global__ void k_chol_small(int c, const double* __restrict__ G, double* __restrict__ Rout, int* info_out,
                              const double* __restrict__ nb2, int nb2_stride, int* flag_out,
-                             const int* __restrict__ pred, int want) {
+                             const int* __restrict__ pred, int want, int adaptive, double thresh, int* cond_out) {
     if (pred && *pred != want) return;
     __shared__ double A[kMaxC][kMaxC + 1];
     const int lane = threadIdx.x;
-    for (int e = lane; e < c * c; e += 32) A[e % c][e / c] = G[e];     // A[i][j] = G(i,j)
-    __syncwarp();
-    int info = 0;
-    // right-looking upper Cholesky, lane l owns column l
-    for (int j = 0; j < c; ++j) {
-        const double d = A[j][j];
-        if (!(d > 0.0)) { info = j + 1; break; }
-        const double rjj = sqrt(d);
+    double gdiag = (lane < c) ? G[(size_t)lane * c + lane] : 0.0, gmax = gdiag;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+    double shift = 0.0;
+    int info = 0, nshift = 0;
+    while (true) {
+        for (int e = lane; e < c * c; e += 32) A[e % c][e / c] = G[e] + ((e % c == e / c) ? shift : 0.0);     // A[i][j] = G(i,j)
         __syncwarp();
-        if (lane >= j && lane < c) A[j][lane] = (lane == j) ? rjj : A[j][lane] / rjj;
-        __syncwarp();
-        if (lane > j && lane < c) {
-            const double rjl = A[j][lane];
-            for (int i = j + 1; i <= lane; ++i) A[i][lane] = fma(-A[j][i], rjl, A[i][lane]);
+        info = 0;
+        // right-looking upper Cholesky, lane l owns column l
+        for (int j = 0; j < c; ++j) {
+            const double d = A[j][j];
+            if (!(d > 0.0)) { info = j + 1; break; }
+            const double rjj = sqrt(d);
+            __syncwarp();
+            if (lane >= j && lane < c) A[j][lane] = (lane == j) ? rjj : A[j][lane] / rjj;
+            __syncwarp();
+            if (lane > j && lane < c) {
+                const double rjl = A[j][lane];
+                for (int i = j + 1; i <= lane; ++i) A[i][lane] = fma(-A[j][i], rjl, A[i][lane]);
+            }
+            __syncwarp();
         }
+        if (info == 0 || !adaptive || nshift >= 6 || !(gmax > 0.0)) break;
+        ++nshift;
+        shift = (nshift == 1) ? 100.0 * c * 2.220446049250313e-16 * gmax : shift * 100.0;
         __syncwarp();
     }
     for (int e = lane; e < c * c; e += 32) {
         const int i = e % c, j = e / c;
         Rout[e] = (i <= j) ? A[i][j] : 0.0;
     }
-    if (lane == 0 && info_out) *info_out = info;
+    if (lane == 0 && info_out) *info_out = info ? info : -nshift;
     __syncwarp();
+    if (cond_out) {
+        double worst = (lane < c) ? (gdiag > 0.0 ? A[lane][lane] / sqrt(gdiag) : 0.0) : 1.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) worst = fmin(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+        if (lane == 0) *cond_out = (info == 0 && (nshift > 0 || worst < thresh)) ? 1 : 0;
+    }
     if (flag_out) {
         if (info != 0) { if (lane == 0) *flag_out = 0; }
         else norm_drop_flag(c, A, nb2, nb2_stride, flag_out, lane);
@@ -353,9 +373,10 @@ __global__ void k_chol_small(int c, const double* __restrict__ G, double* __rest
 }
 
 int chol_small(calz_ctx* ctx, int c, const double* G_dev, double* R_dev, int* info_out, const double* nb2,
-               int nb2_stride, int* flag_out, const int* pred, int want) {
+               int nb2_stride, int* flag_out, const int* pred, int want, bool adaptive, int* cond_out) {
     if (c > kMaxC) return set_error(ctx, CALZ_ERR_UNSUPPORTED, "block width c=%d > %d", c, kMaxC);
-    k_chol_small<<<1, 32, 0, ctx->stream>>>(c, G_dev, R_dev, info_out, nb2, nb2_stride, nb2 ? flag_out : nullptr, pred, want);
+    k_chol_small<<<1, 32, 0, ctx->stream>>>(c, G_dev, R_dev, info_out, nb2, nb2_stride, nb2 ? flag_out : nullptr, pred, want,
+                                            adaptive ? 1 : 0, 1.0 / (double)ctx->opt_cholqr2_inv_thresh, cond_out);
     CALZ_LAUNCH_CHECK(ctx);
     return CALZ_OK;
 }
@@ -374,29 +395,21 @@ int norm_drop_decision(calz_ctx* ctx, int c, const double* R_dev, const double* 
     return CALZ_OK;
 }
 
+// Rfin = *sel ? R_b : R_a ; *reorth_out = *sel ? *cond_b : *cond_a
 __global__ void k_select_r(int c, const double* __restrict__ Ra, const double* __restrict__ Rb, const int* __restrict__ sel,
-                           const double* __restrict__ G, double* __restrict__ Rfin, int* reorth_out, int adaptive, double thresh) {
-    const double* R = (sel && *sel) ? Rb : Ra;
-    const int lane = threadIdx.x;
-    for (int e = lane; e < c * c; e += 32) Rfin[e] = R[e];
-    if (reorth_out) {
-        // sine of the angle between column j and the span of the previous ones; 1/min is a lower bound of the
-        // equilibrated condition number, which is what governs the accuracy of a Cholesky-based QR
-        double worst = 1.0;
-        if (adaptive && lane < c) {
-            const double gjj = G[(size_t)lane * c + lane];
-            worst = gjj > 0.0 ? R[(size_t)lane * c + lane] / sqrt(gjj) : 0.0;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) worst = fmin(worst, __shfl_xor_sync(0xffffffffu, worst, o));
-        if (lane == 0) *reorth_out = (adaptive && worst < thresh) ? 1 : 0;
+                           const int* __restrict__ cond_a, const int* __restrict__ cond_b, double* __restrict__ Rfin, int* reorth_out) {
+    const bool second = sel && *sel;
+    const double* R = second ? Rb : Ra;
+    for (int e = threadIdx.x; e < c * c; e += 32) Rfin[e] = R[e];
+    if (reorth_out && threadIdx.x == 0) {
+        const int* cnd = second ? cond_b : cond_a;
+        *reorth_out = cnd ? *cnd : 0;
     }
 }
 
-int select_r(calz_ctx* ctx, int c, const double* R_a, const double* R_b, const int* sel, const double* G, double* Rfin,
-             int* reorth_out, bool adaptive) {
-    k_select_r<<<1, 32, 0, ctx->stream>>>(c, R_a, R_b, sel, G, Rfin, reorth_out, adaptive ? 1 : 0,
-                                          1.0 / (double)ctx->opt_cholqr2_inv_thresh);
+int select_r(calz_ctx* ctx, int c, const double* R_a, const double* R_b, const int* sel, const int* cond_a, const int* cond_b,
+             double* Rfin, int* reorth_out) {
+    k_select_r<<<1, 32, 0, ctx->stream>>>(c, R_a, R_b, sel, cond_a, cond_b, Rfin, reorth_out);
     CALZ_LAUNCH_CHECK(ctx);
     return CALZ_OK;
 }

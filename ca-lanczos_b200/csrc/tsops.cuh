@@ -37,16 +37,17 @@ int ts_update(calz_ctx* ctx, int64_t n, const double* Q, int64_t ldQ, int M, con
 int ts_trsolve(calz_ctx* ctx, int64_t n, int c, const double* X, int64_t ldX, const double* R, double* Q,
                int64_t ldQ, const int* pred, int want);
 
-// Rfin = *sel ? R_b : R_a;  *reorth_out = adaptive && min_j Rfin_jj / sqrt(G_jj) < 1/inv_thresh
-int select_r(calz_ctx* ctx, int c, const double* R_a, const double* R_b, const int* sel, const double* G,
-             double* Rfin, int* reorth_out, bool adaptive);
+// Rfin = *sel ? R_b : R_a;  *reorth_out = *sel ? *cond_b : *cond_a  (cond_* from chol_small, may be NULL)
+int select_r(calz_ctx* ctx, int c, const double* R_a, const double* R_b, const int* sel, const int* cond_a,
+             const int* cond_b, double* Rfin, int* reorth_out);
 // Rfin = Rb * Rfin (upper triangular product), predicated
 int rmul_upper(calz_ctx* ctx, int c, const double* Rb, double* Rfin, const int* pred, int want);
 
 // R = chol(G) on the device (one warp), optional norm-drop decision of projectAndNormalize.m:45-52:
 // *flag_out = max_i |sqrt(nb2[i*nb2_stride]) - ||R(:,i)|| | / sqrt(nb2[...]) > 0.5.  info_out: 0 or failing pivot.
+// adaptive (CALZ_QR_CHOLQR2): shifted retry on breakdown (info_out = -#shifts), cond_out = "needs another CholQR pass".
 int chol_small(calz_ctx* ctx, int c, const double* G_dev, double* R_dev, int* info_out, const double* nb2,
-               int nb2_stride, int* flag_out, const int* pred, int want);
+               int nb2_stride, int* flag_out, const int* pred, int want, bool adaptive = false, int* cond_out = nullptr);
 
 // same decision for a backend that already has R on the device (TSQR)
 int norm_drop_decision(calz_ctx* ctx, int c, const double* R_dev, const double* nb2, int nb2_stride, int* flag_out);

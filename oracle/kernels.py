@@ -86,19 +86,40 @@ def cholqr(X):
     return np.asfortranarray(Q), np.asfortranarray(R)
 
 
+def _chol_shifted(G, adaptive=True):
+    """Upper Cholesky factor; on breakdown retry with G + shift*I (shift = 100*c*eps*max(diag G), x100 per retry)."""
+    c = G.shape[0]
+    shift, nshift = 0.0, 0
+    while True:
+        try:
+            return np.linalg.cholesky(G + shift * np.eye(c)).T, nshift
+        except np.linalg.LinAlgError:
+            if not adaptive or nshift >= 6:
+                raise
+            nshift += 1
+            shift = 100.0 * c * 2.220446049250313e-16 * np.max(np.diag(G)) if nshift == 1 else shift * 100.0
+
+
 def cholqr2(X, inv_thresh=32.0):
-    """NOT in the reference: cholqr.m followed by an automatic second CholQR pass (R = R2*R1) when
-    min_j R_jj/||x_j|| < 1/inv_thresh -- the restatement of libcalz' CALZ_QR_CHOLQR2 backend, kept here so the tests
-    can check that the device takes the same branch.  Its results are compared against tsqr (Householder)."""
+    """NOT in the reference: cholqr.m made robust -- the restatement of libcalz' CALZ_QR_CHOLQR2 backend.  One CholQR
+    pass (shifted if the Cholesky breaks down); while min_j R_jj/||x_j|| < 1/inv_thresh or a shift was needed, repeat
+    CholQR on Q (at most 3 more passes), R = R_k ... R_1.  Checked against tsqr (Householder) in the tests."""
     X = np.asarray(X)
-    G = X.T @ X
-    R1 = np.linalg.cholesky(G).T
-    Q = sla.solve_triangular(R1, X.T, trans="T", lower=False).T
-    if np.min(np.diag(R1) / np.sqrt(np.diag(G))) < 1.0 / inv_thresh:
-        R2 = np.linalg.cholesky(Q.T @ Q).T
-        Q = sla.solve_triangular(R2, Q.T, trans="T", lower=False).T
-        R1 = R2 @ R1
-    return np.asfortranarray(Q), np.asfortranarray(R1)
+
+    def one_pass(Y):
+        G = Y.T @ Y
+        R, nshift = _chol_shifted(G)
+        Q = sla.solve_triangular(R, Y.T, trans="T", lower=False).T
+        again = nshift > 0 or np.min(np.diag(R) / np.sqrt(np.diag(G))) < 1.0 / inv_thresh
+        return Q, R, again
+
+    Q, R, again = one_pass(X)
+    for _ in range(3):
+        if not again:
+            break
+        Q, R2, again = one_pass(Q)
+        R = R2 @ R
+    return np.asfortranarray(Q), np.asfortranarray(R)
 
 
 def normalize(X, opt="None", tol=1.0e-8, backend="tsqr"):

@@ -77,7 +77,7 @@ def test_cholqr_not_positive_definite_raises():
         api.projectAndNormalize([], X, True, backend="cholqr")
 
 
-@pytest.mark.parametrize("n,c,scale", [(20000, 8, 1.0), (20000, 8, 1e-5), (50000, 9, 2e-6), (3000, 17, 1e-5)])
+@pytest.mark.parametrize("n,c,scale", [(20000, 8, 1.0), (20000, 8, 1e-5), (50000, 9, 2e-6), (50000, 9, 3e-8), (3000, 17, 1e-5)])
 def test_cholqr2_is_householder_accurate(n, c, scale):
     # ill-conditioned block: X = [x1, x1 + scale*noise, ...]: kappa_eq ~ 1/scale.  One CholQR pass loses kappa^2*eps of
     # orthogonality; the CHOLQR2 backend detects it on the device and re-orthogonalises, matching Householder.
@@ -87,7 +87,7 @@ def test_cholqr2_is_householder_accurate(n, c, scale):
     Qo, Ro = kernels.tsqr(X)
     Qr, Rr = kernels.cholqr2(X)
     keq = np.linalg.cond(X / np.linalg.norm(X, axis=0))
-    assert orth(Q2) < 1e-13 * c
+    assert orth(Q2) < (1e-13 * c if keq < 1e9 else 1e-10)        # three refinement passes at most
     assert rel(Q2 @ R2, X) < 1e-14 * c
     assert rel(R2, Ro) < max(1e-13, 100 * keq * EPS)
     assert rel(R2, Rr) < max(1e-13, 100 * keq * EPS)
