@@ -1,0 +1,113 @@
+"""Multi-GPU parity check, one process per GPU (launched by torchrun):
+
+    torchrun --nproc-per-node P tests/dist_check.py [--m 48]
+
+Every rank builds its row slab (+ level-s ghost rows) of the 3-D Laplacian, runs the device-resident block pipeline
+with a P-rank communicator, and rank 0 compares against the 1-way oracle: ghost index sets / exchange lists bit-exact
+(oracle/partition.py), basis vectors, T entries, Ritz values, orthogonality.  Exit code != 0 on any mismatch.
+Used by tests/test_gpu_dist.py (needs >= 2 GPUs) and run by hand with `gpurun --gpus 2`.
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ca_lanczos_b200 import api, gallery
+from ca_lanczos_b200.engine import BlockEngine
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--m", type=int, default=40)
+    ap.add_argument("--mz", type=int, default=0)
+    ap.add_argument("--s", type=int, default=8)
+    ap.add_argument("--blocks", type=int, default=5)
+    ap.add_argument("--backend", default="cholqr2")
+    args = ap.parse_args()
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ctx = api.Context(local)
+    ids = [api.Context.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    ctx.init_comm(world, rank, ids[0])
+
+    m, s = args.m, args.s
+    mz = args.mz or m
+    n, plane = m * m * mz, m * m
+    lo, hi = (rank * n) // world, ((rank + 1) * n) // world
+    # supply exactly the level-(s) closure hull of a stencil: s planes either side (clipped)
+    have_lo, have_hi = max(0, lo - s * plane - plane), min(n, hi + s * plane + plane)
+    A_rows = gallery.laplace3d(m, m, mz, row_lo=have_lo, row_hi=have_hi)
+    dm = api.DeviceMatrix(A_rows, s_max=s, layout="sell", ctx=ctx, n_glob=n, row_begin=have_lo)
+    fails = []
+
+    def check(name, ok, detail=""):
+        if not ok:
+            fails.append("rank %d: %s %s" % (rank, name, detail))
+
+    # ---- integer objects: bit-exact against the oracle
+    from oracle import partition
+    A = gallery.laplace3d(m, m, mz)
+    b = partition.row_bounds(n, world)
+    check("row bounds", (dm.info("row_lo"), dm.info("row_hi")) == (int(b[rank]), int(b[rank + 1])))
+    ghosts = partition.ghost_indices(A, lo, hi, s)
+    check("ghost set", np.array_equal(dm.ghost_indices(), ghosts), "%d vs %d" % (dm.ghost_indices().size, ghosts.size))
+    lists = partition.exchange_lists(A, world, s)
+    for q in range(world):
+        check("recv list from %d" % q, np.array_equal(dm.recv_list(q), lists[rank][q]))
+        check("send list to %d" % q, np.array_equal(dm.send_list(q), lists[q][rank]))
+
+    # ---- block pipeline vs the 1-way oracle driver
+    from oracle import drivers, kernels
+    r = np.cos(0.61 * np.arange(n) ** 1.5) + 0.3 * np.sin(1.7 * np.arange(n))
+    shifts = gallery.leja_points(0.0, 12.0, s)
+    Bk = np.zeros((s + 1, s)); Bk[np.arange(s), np.arange(s)] = shifts; Bk[np.arange(1, s + 1), np.arange(s)] = 1.0
+    io = {}
+    To, Qo = drivers.ca_lanczos(A, r, s, s * args.blocks, "newton", "local", Bk=Bk, info=io)
+    q0 = (r / np.sqrt(r @ r))[lo:hi]
+    eng = BlockEngine(dm, s, args.blocks + 1, "newton", shifts, args.backend)
+    eng.first_block(q0)
+    for _ in range(args.blocks - 1):
+        eng.next_block()
+    T = eng.T_matrix()
+    Qloc = eng.Q_host()
+    sc = np.abs(To).max()
+    check("second-pass pattern", eng.second == [i["second_pass"] for i in io["pan"]], str(eng.second))
+    check("T entries 1e-10", np.abs(T - To).max() <= 1e-10 * sc, "%.3e" % (np.abs(T - To).max() / sc))
+    ro = np.sort(np.linalg.eig(To)[0].real)[::-1]; rg = np.sort(np.linalg.eig(T)[0].real)[::-1]
+    check("ritz 1e-8", np.max(np.abs(rg[:4] - ro[:4]) / np.abs(ro[:4])) < 1e-8)
+    err = np.max(np.linalg.norm(Qloc - Qo[lo:hi, : Qloc.shape[1]], axis=0))
+    check("Q rows 1e-10", err < 1e-10, "%.3e" % err)
+    # MPK alone, through the host flavour with the communicator (owned rows in, owned rows out)
+    v = r / np.sqrt(r @ r)
+    V = api.matrix_powers_newton(dm, v[lo:hi], s, shifts, 1)
+    Vo = kernels.matrix_powers_newton(A, v, s, shifts, 1)
+    e = np.max(np.linalg.norm(V - Vo[lo:hi], axis=0) / np.linalg.norm(Vo[lo:hi], axis=0))
+    check("mpk owned rows 1e-13", e < 1e-13, "%.3e" % e)
+    # identical small results on every rank (deterministic reductions)
+    t = torch.tensor(T.ravel(), device=dev)
+    t0 = t.clone()
+    dist.broadcast(t0, src=0)
+    check("T identical on all ranks", bool(torch.equal(t, t0)))
+
+    allf = [None] * world
+    dist.all_gather_object(allf, fails)
+    if rank == 0:
+        flat = [f for fs in allf for f in fs]
+        print("dist_check P=%d m=%dx%dx%d s=%d backend=%s: %s" % (world, m, m, mz, s, args.backend, "OK" if not flat else "FAILED"))
+        print("  max |T-To|/max|To| = %.2e, Q rows err %.2e, mpk err %.2e, ghosts %d" % (np.abs(T - To).max() / sc, err, e, ghosts.size))
+        for f in flat:
+            print("  " + f)
+    dist.destroy_process_group()
+    sys.exit(1 if any(allf) and any(len(x) for x in allf) else 0)
+
+
+if __name__ == "__main__":
+    main()
