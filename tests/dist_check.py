@@ -1,6 +1,6 @@
 """Multi-GPU parity check, one process per GPU (launched by torchrun):
 
-    torchrun --nproc-per-node P tests/dist_check.py [--m 48]
+    torchrun --nproc-per-node P tests/dist_check.py [--grid 48]
 
 Every rank builds its row slab (+ level-s ghost rows) of the 3-D Laplacian, runs the device-resident block pipeline
 with a P-rank communicator, and rank 0 compares against the 1-way oracle: ghost index sets / exchange lists bit-exact
@@ -23,8 +23,8 @@ from ca_lanczos_b200.engine import BlockEngine
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--m", type=int, default=40)
-    ap.add_argument("--mz", type=int, default=0)
+    ap.add_argument("--grid", type=int, default=40)
+    ap.add_argument("--gridz", type=int, default=0)
     ap.add_argument("--s", type=int, default=8)
     ap.add_argument("--blocks", type=int, default=5)
     ap.add_argument("--backend", default="cholqr2")
@@ -38,8 +38,8 @@ def main():
     dist.broadcast_object_list(ids, src=0)
     ctx.init_comm(world, rank, ids[0])
 
-    m, s = args.m, args.s
-    mz = args.mz or m
+    m, s = args.grid, args.s
+    mz = args.gridz or m
     n, plane = m * m * mz, m * m
     lo, hi = (rank * n) // world, ((rank + 1) * n) // world
     # supply exactly the level-(s) closure hull of a stencil: s planes either side (clipped)

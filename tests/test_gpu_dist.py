@@ -22,6 +22,6 @@ def test_two_rank_pipeline_matches_one_way_oracle(backend):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-           "--master-port", "29541", os.path.join(ROOT, "tests", "dist_check.py"), "--m", "32", "--backend", backend]
+           "--master-port", "29541", os.path.join(ROOT, "tests", "dist_check.py"), "--grid", "32", "--backend", backend]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
