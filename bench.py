@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--l2-chunk-mb", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     return ap.parse_args()
 
@@ -66,47 +67,53 @@ def workload_name(m, s, backend):
 
 # ----------------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """SM clock and throttle reasons sampled every ~5 ms DURING the timed region through NVML (the same counters
-    `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints; a 200 ms nvidia-smi loop is too coarse for a
-    ~100 ms timed region)."""
+    """SM clock and throttle reasons sampled DURING the timed region by a separate `nvidia-smi -lms 20` process (the recipe
+    of B200_PROFILING.md).  A separate process on purpose: an in-process NVML polling thread competes with the launching
+    thread for the GIL and the driver and was measured to perturb the 2-rank run."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index=0):
-        self.sm, self.reasons, self.max_mhz, self.err = [], set(), None, None
-        self._stop = threading.Event()
+    def __init__(self, index=0, enabled=True):
+        self.rows, self.proc = [], None
+        if not enabled:
+            return
         try:
-            import pynvml
-            pynvml.nvmlInit()
-            self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
-            self.t = threading.Thread(target=self._loop, daemon=True)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
-        except Exception as e:          # noqa: BLE001
-            self.nv, self.err = None, repr(e)
+        except Exception:
+            self.proc = None
 
-    def _loop(self):
-        nv = self.nv
-        names = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80, "sw_power_cap": 0x4}
-        while not self._stop.is_set():
-            try:
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
-                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for k, bit in names.items():
-                    if r & bit:
-                        self.reasons.add(k)
-            except Exception as e:      # noqa: BLE001
-                self.err = repr(e)
-                return
-            time.sleep(0.005)
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        self.t0 = time.perf_counter()
 
     def stop(self):
-        if self.nv is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
-        self._stop.set()
-        self.t.join(timeout=1.0)
-        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.sm)}
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled"]}
+        t1 = time.perf_counter()
+        time.sleep(0.05)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        t0 = getattr(self, "t0", 0.0)
+        rows = [r for (t, r) in self.rows if t0 <= t <= t1 + 0.03] or [r for (_, r) in self.rows[-3:]]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # ----------------------------------------------------------------------------------------------------- CPU arm
@@ -227,8 +234,12 @@ def run_b200(args):
     # ---- timed region: exactly K blocks, CUDA events on libcalz' stream, per-phase events for the roofline
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     eng.phase_events = None
+    sampler = ClockSampler(local, enabled=not args.no_clocks) if rank == 0 else None
+    if sampler:
+        time.sleep(0.3)                       # let nvidia-smi start before the timed region
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     ctx.launch_count(reset=True)
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record(stream)
