@@ -60,6 +60,7 @@ struct calz_ctx {
     int64_t opt_sell_sigma = 0;      // 0: choose
     int64_t opt_csr_lanes = 0;       // 0: choose
     int64_t opt_cholqr2_inv_thresh = 32;
+    int64_t opt_tile_pipeline = 1;   // fused TMA-tile passes in projectAndNormalize (0: legacy kernels)
     int64_t opt_grid_mult = 8;       // CTAs per SM for the persistent tall-skinny kernels
 
     // scratch

@@ -205,7 +205,8 @@ int calz_project(calz_ctx* ctx, int64_t n, int nblk, const double* const* Qblk, 
 int calz_project_and_normalize(calz_ctx* ctx, int64_t n, int nblk, const double* const* Qblk, const int64_t* ldQ,
                                const int* mcols, int c, const double* X, int64_t ldX, int doreorth, int backend,
                                double* QZ, int64_t ldQZ, double* const* Rblk, double* Rlast, int* second_pass, int* rank) {
-    if (!ctx || !X || !QZ || n < 1 || c < 1 || c > kMaxC || nblk < 0 || (backend != CALZ_QR_TSQR && backend != CALZ_QR_CHOLQR && backend != CALZ_QR_CHOLQR2))
+    if (!ctx || !X || !QZ || n < 1 || c < 1 || c > kMaxC || nblk < 0 ||
+        (backend != CALZ_QR_TSQR && backend != CALZ_QR_CHOLQR && backend != CALZ_QR_CHOLQR2))
         return set_error(ctx, CALZ_ERR_BADARG, "calz_project_and_normalize: bad arguments");
     if (QZ == X) return set_error(ctx, CALZ_ERR_BADARG, "calz_project_and_normalize: QZ must not alias X");
     CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -216,60 +217,83 @@ int calz_project_and_normalize(calz_ctx* ctx, int64_t n, int nblk, const double*
         if (!empty_block(Qblk, mcols, i)) blocks.push_back(i);
     const int nb = (int)blocks.size();
     const bool fuse_norms = doreorth && nb > 0;        // column norms of X ride along with the first coefficient sweep
+    // fused tile pipeline (tiles.cu): one previous block, Cholesky-based QR, TMA-compatible alignment
+    const bool tiled = nb == 1 && fuse_norms && backend != CALZ_QR_TSQR && ctx->opt_tile_pipeline &&
+                       tile_path_ok(n, Qblk[blocks[0]], ldQ[blocks[0]], mcols[blocks[0]], X, ldX, c, QZ, ldQZ);
     size_t doubles = 8;                                // flags
     std::vector<size_t> off1(nb), off2(nb);
-    std::vector<int> ld1(nb);
+    std::vector<int> ld1(nb), ld2(nb);
     for (int k = 0; k < nb; ++k) {
         const int m = mcols[blocks[k]];
         ld1[k] = (k == 0 && fuse_norms) ? m + c : m;
         off1[k] = doubles; doubles += (size_t)ld1[k] * c;
     }
-    for (int k = 0; k < nb; ++k) { off2[k] = doubles; doubles += (size_t)mcols[blocks[k]] * c; }
+    for (int k = 0; k < nb; ++k) {
+        ld2[k] = tiled ? mcols[blocks[k]] + c : mcols[blocks[k]];
+        off2[k] = doubles; doubles += (size_t)ld2[k] * c;
+    }
+    const size_t offS3 = doubles; doubles += tiled ? (size_t)(mcols[blocks[0]] + c) * c : 0;
     const size_t offG = doubles; doubles += (size_t)c * c;
     const size_t offR1 = doubles; doubles += (size_t)c * c;
     const size_t offR2 = doubles; doubles += (size_t)c * c;
     const size_t offRf = doubles; doubles += (size_t)c * c;       // R of the last normalize (what the host reads)
-    const size_t offG2 = doubles; doubles += (size_t)c * c;       // CholQR2 scratch
-    const size_t offRb = doubles; doubles += (size_t)c * c;
+    const size_t offG2 = doubles; doubles += 2 * (size_t)c * c;   // CholQR2 refinement scratch
     double* sm;
     CALZ_TRY(small_scratch(ctx, doubles, &sm));
     int* flags = (int*)sm;
-    CALZ_CUDA(ctx, cudaMemsetAsync(sm, 0, 8 * sizeof(double), ctx->stream));
+    CALZ_CUDA(ctx, cudaMemsetAsync(sm, 0, doubles * sizeof(double), ctx->stream));
     double *G = sm + offG, *R1 = sm + offR1, *R2 = sm + offR2, *Rf = sm + offRf;
+    // flags: [0] second pass, [1]/[2] chol info pass 1/2, [3]/[4] conditioning flag pass 1/2, [5] selected, [6..7] refinement
 
-    // ---- pass 1: Y = X - sum_i Q_i (Q_i' X)   (sequential over blocks, project.m:32-39); Y lives in QZ
     const double* src = X;
     int64_t ldsrc = ldX;
-    for (int k = 0; k < nb; ++k) {
-        const int i = blocks[k], m = mcols[i];
-        Panels A = one_panel(Qblk[i], ldQ[i], m);
-        if (k == 0 && fuse_norms) add_panel(A, X, ldX, c);          // [Q_1 X]' X: last c rows hold X'X
-        double* C = sm + off1[k];
-        CALZ_TRY(tsmm_tn(ctx, n, A, src, ldsrc, c, C, ld1[k], false, nullptr, 0, true));
-        CALZ_TRY(ts_update(ctx, n, Qblk[i], ldQ[i], m, C, ld1[k], src, ldsrc, c, QZ, ldQZ, nullptr, 0));
+    if (tiled) {
+        const int i = blocks[0], m = mcols[i], ldS = m + c;
+        double *S1 = sm + off1[0], *S2 = sm + off2[0], *S3 = sm + offS3;
+        // pass 1: S1 = [Q X]'X  -> C1 and ||x_i||^2
+        CALZ_TRY(tile_pass(ctx, 0, n, Qblk[i], ldQ[i], m, X, ldX, c, nullptr, 0, nullptr, 0, S1, ldS, nullptr, 0, true));
+        // pass 2: Y = X - Q*C1 (into QZ), S2 = [Q Y]'Y -> C2 (used only if pass 2 of the reference fires) and G_Y
+        CALZ_TRY(tile_pass(ctx, 1, n, Qblk[i], ldQ[i], m, X, ldX, c, S1, ldS, QZ, ldQZ, S2, ldS, nullptr, 0, true));
+        CALZ_TRY(chol_small(ctx, c, S2 + m, R1, flags + 1, S1 + m, ldS + 1, flags + 0, nullptr, 0, backend == CALZ_QR_CHOLQR2,
+                            backend == CALZ_QR_CHOLQR2 ? flags + 3 : nullptr, ldS));
+        // pass 3 (iff the norm-drop test fired): Z = Y - Q*C2 in place, S3 = Z'Z
+        CALZ_TRY(tile_pass(ctx, 2, n, Qblk[i], ldQ[i], m, QZ, ldQZ, c, S2, ldS, QZ, ldQZ, S3, ldS, flags, 1, true));
+        CALZ_TRY(chol_small(ctx, c, S3 + m, R2, flags + 2, nullptr, 0, nullptr, flags, 1, backend == CALZ_QR_CHOLQR2,
+                            backend == CALZ_QR_CHOLQR2 ? flags + 4 : nullptr, ldS));
         src = QZ;
         ldsrc = ldQZ;
-    }
-    // nb2_i = ||X(:,i)||^2: diagonal of the X'X block of the fused sweep
-    const double* nb2 = nullptr;
-    int nb2_stride = 0;
-    if (fuse_norms) {
-        nb2 = sm + off1[0] + mcols[blocks[0]];
-        nb2_stride = ld1[0] + 1;
-    }
-    // ---- normalize(Y): R1 (+ the norm-drop decision on the device)
-    // flags: [0] second pass, [1]/[2] chol info pass 1/2, [3]/[4] conditioning flag pass 1/2, [5] selected, [6..7] refinement
-    CALZ_TRY(factor_r(ctx, backend, n, c, src, ldsrc, G, R1, flags + 1, nb2, nb2_stride, flags + 0, nullptr, 0, flags + 3));
-
-    // ---- pass 2, predicated on flags[0] == 1 (projectAndNormalize.m:61-73): Z = Y - sum_i Q_i (Q_i' Y), in place
-    if (fuse_norms) {
+    } else {
+        // ---- pass 1: Y = X - sum_i Q_i (Q_i' X)   (sequential over blocks, project.m:32-39); Y lives in QZ
         for (int k = 0; k < nb; ++k) {
             const int i = blocks[k], m = mcols[i];
-            double* C = sm + off2[k];
-            CALZ_TRY(tsmm_tn(ctx, n, one_panel(Qblk[i], ldQ[i], m), QZ, ldQZ, c, C, m, false, flags, 1, true));
-            CALZ_TRY(ts_update(ctx, n, Qblk[i], ldQ[i], m, C, m, QZ, ldQZ, c, QZ, ldQZ, flags, 1));
+            Panels A = one_panel(Qblk[i], ldQ[i], m);
+            if (k == 0 && fuse_norms) add_panel(A, X, ldX, c);          // [Q_1 X]' X: last c rows hold X'X
+            double* C = sm + off1[k];
+            CALZ_TRY(tsmm_tn(ctx, n, A, src, ldsrc, c, C, ld1[k], false, nullptr, 0, true));
+            CALZ_TRY(ts_update(ctx, n, Qblk[i], ldQ[i], m, C, ld1[k], src, ldsrc, c, QZ, ldQZ, nullptr, 0));
+            src = QZ;
+            ldsrc = ldQZ;
         }
-        CALZ_TRY(factor_r(ctx, backend, n, c, QZ, ldQZ, G, R2, flags + 2, nullptr, 0, nullptr, flags, 1, flags + 4));
+        // nb2_i = ||X(:,i)||^2: diagonal of the X'X block of the fused sweep
+        const double* nb2 = nullptr;
+        int nb2_stride = 0;
+        if (fuse_norms) {
+            nb2 = sm + off1[0] + mcols[blocks[0]];
+            nb2_stride = ld1[0] + 1;
+        }
+        // ---- normalize(Y): R1 (+ the norm-drop decision on the device)
+        CALZ_TRY(factor_r(ctx, backend, n, c, src, ldsrc, G, R1, flags + 1, nb2, nb2_stride, flags + 0, nullptr, 0, flags + 3));
+
+        // ---- pass 2, predicated on flags[0] == 1 (projectAndNormalize.m:61-73): Z = Y - sum_i Q_i (Q_i' Y), in place
+        if (fuse_norms) {
+            for (int k = 0; k < nb; ++k) {
+                const int i = blocks[k], m = mcols[i];
+                double* C = sm + off2[k];
+                CALZ_TRY(tsmm_tn(ctx, n, one_panel(Qblk[i], ldQ[i], m), QZ, ldQZ, c, C, m, false, flags, 1, true));
+                CALZ_TRY(ts_update(ctx, n, Qblk[i], ldQ[i], m, C, m, QZ, ldQZ, c, QZ, ldQZ, flags, 1));
+            }
+            CALZ_TRY(factor_r(ctx, backend, n, c, QZ, ldQZ, G, R2, flags + 2, nullptr, 0, nullptr, flags, 1, flags + 4));
+        }
     }
     // ---- Q of the LAST normalize only
     if (backend != CALZ_QR_TSQR) {
@@ -302,7 +326,7 @@ int calz_project_and_normalize(calz_ctx* ctx, int64_t n, int nblk, const double*
         for (int j = 0; j < c; ++j)
             for (int a = 0; a < m; ++a) {
                 double v = h[off1[k] + (size_t)j * ld1[k] + a];
-                if (second) v = h[off2[k] + (size_t)j * m + a] + v;      // RZ{i} = RZ{i} + RY{i}  (:71-73)
+                if (second) v = h[off2[k] + (size_t)j * ld2[k] + a] + v;      // RZ{i} = RZ{i} + RY{i}  (:71-73)
                 Rblk[i][(size_t)j * m + a] = v;
             }
     }

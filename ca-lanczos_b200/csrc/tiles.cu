@@ -1,0 +1,316 @@
+// Fused projectAndNormalize passes on TMA-staged row tiles (the steady-state block of ca_lanczos_basic).
+//
+// One persistent CTA per resident slot streams 128-row tiles of the tall-skinny operands [Q | X] through a
+// multi-stage shared-memory ring: a producer warp issues one 1-D TMA bulk copy (cp.async.bulk, mbarrier
+// complete_tx) per column, 8 consumer warps
+//   - (update modes) apply  Y = X - Q*C  one row per thread pair straight in shared memory and stream Y back to HBM,
+//   - contract the tile over its rows with fp64 DMMA (mma.sync m8n8k4), fragments read conflict-free from
+//     shared memory (column pitch 132 doubles),
+// so every operand crosses HBM exactly once per pass:
+//   pass 1  COEFF   S1 = [Q X]'X               -> C1 = Q'X (project.m:34) and diag(X'X) = ||x_i||^2 (pAN.m:17-22)
+//   pass 2  UPDATE  Y = X - Q*C1 (project.m:35), S2 = [Q Y]'Y -> C2 = Q'Y (2nd pass, pAN.m:63) and G_Y = Y'Y (cholqr.m:5)
+//   pass 3  UPDATE  Z = Y - Q*C2 in place,      S3 = Z'Z       (cholqr.m:5 of the second normalize, pAN.m:64)
+// Reductions are deterministic: fixed warp order inside the CTA, per-CTA partials, last CTA sums them in a fixed order.
+#include <algorithm>
+
+#include "tsops.cuh"
+
+namespace calz {
+
+namespace {
+
+constexpr int kTileRows = 128;
+constexpr int kPitch = 132;                     // doubles per column slot: 132 mod 16 == 4 => conflict-free DMMA fragments
+constexpr int kConsumerWarps = 8;
+constexpr int kTileThreads = (kConsumerWarps + 1) * 32;
+
+enum { MODE_COEFF = 0, MODE_UPDATE_FULL = 1, MODE_UPDATE_GRAM = 2 };
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory"); }
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+struct TileArgs {
+    long long n;
+    const double* Q; long long ldQ; int M;          // A panel (previous block)
+    const double* X; long long ldX; int c;          // block being orthogonalised (input of this pass)
+    double* Y; long long ldY;                       // update modes: where the updated block goes (may alias X)
+    const double* C; int ldC;                       // update modes: coefficients (M x c, device)
+    double* S; int ldS;                             // result: rows [0,M) = Q-part, rows [M, M+c) = block-part  (x c columns)
+    double* partials; unsigned int* ticket;
+    const int* pred; int want;
+};
+
+// dynamic shared memory layout: [stages][slots][kPitch] doubles | Cs[M][8*CT] | red | barriers
+template <int MT, int CT, int MODE>
+__global__ void __launch_bounds__(kTileThreads, 1)
+k_tile(TileArgs p, int stages) {
+    if (p.pred && *p.pred != p.want) return;
+    constexpr int SLOTS = 8 * (MT + CT);
+    constexpr bool ACC_Q = (MODE != MODE_UPDATE_GRAM);           // accumulate the Q-row tiles too
+    constexpr int RT0 = ACC_Q ? 0 : MT;                           // first row-tile that is accumulated
+    constexpr int NRT = MT + CT - RT0;
+    constexpr int CW = 8 * CT;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* tiles = reinterpret_cast<double*>(smem_raw);
+    const size_t stage_doubles = (size_t)SLOTS * kPitch;
+    double* Cs = tiles + (size_t)stages * stage_doubles;          // [MT*8][CW]
+    double* red = Cs + (size_t)MT * 8 * CW;                       // [kConsumerWarps][NRT*CT*64]
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + (size_t)kConsumerWarps * NRT * CT * 64);
+    uint64_t* empty = full + stages;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long ntiles = (p.n + kTileRows - 1) / kTileRows;
+
+    // ---- one-time set-up: barriers, zero the padding slots, stage C
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
+        fence_barrier_init();
+    }
+    for (size_t e = tid; e < (size_t)stages * stage_doubles; e += kTileThreads) {
+        const int slot = (int)((e % stage_doubles) / kPitch);
+        const bool used = (slot < 8 * MT) ? (slot < p.M) : (slot - 8 * MT < p.c);
+        if (!used) tiles[e] = 0.0;
+    }
+    if (MODE != MODE_COEFF)
+        for (int e = tid; e < MT * 8 * CW; e += kTileThreads) {
+            const int m = e / CW, j = e % CW;
+            Cs[e] = (m < p.M && j < p.c) ? p.C[(size_t)j * p.ldC + m] : 0.0;
+        }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // =========================================================== producer warp
+        int it = 0;
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int s = it % stages;
+            const uint32_t ph = (uint32_t)((it / stages) & 1);
+            mbar_wait(&empty[s], ph ^ 1);
+            double* dst = tiles + (size_t)s * stage_doubles;
+            const long long r0 = t * kTileRows;
+            const int valid = (int)min((long long)kTileRows, p.n - r0);
+            if (valid == kTileRows) {
+                if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)((p.M + p.c) * kTileRows * sizeof(double)));
+                __syncwarp();
+                for (int col = lane; col < p.M + p.c; col += 32) {
+                    const bool isq = col < p.M;
+                    const double* src = isq ? p.Q + (long long)col * p.ldQ + r0 : p.X + (long long)(col - p.M) * p.ldX + r0;
+                    const int slot = isq ? col : 8 * MT + (col - p.M);
+                    tma_bulk_g2s(dst + (size_t)slot * kPitch, src, kTileRows * sizeof(double), &full[s]);
+                }
+            } else {
+                // ragged last tile: plain loads, zero fill, then a plain arrive
+                for (int e = lane; e < (p.M + p.c) * kTileRows; e += 32) {
+                    const int col = e / kTileRows, r = e % kTileRows;
+                    const bool isq = col < p.M;
+                    const int slot = isq ? col : 8 * MT + (col - p.M);
+                    double v = 0.0;
+                    if (r < valid) v = isq ? p.Q[(long long)col * p.ldQ + r0 + r] : p.X[(long long)(col - p.M) * p.ldX + r0 + r];
+                    dst[(size_t)slot * kPitch + r] = v;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full[s]);
+            }
+        }
+    } else {
+        // =========================================================== consumer warps
+        const int g = lane >> 2, tq = lane & 3;
+        double acc[NRT][CT][2];
+#pragma unroll
+        for (int a = 0; a < NRT; ++a)
+#pragma unroll
+            for (int b = 0; b < CT; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        int it = 0;
+        for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
+            const int s = it % stages;
+            const uint32_t ph = (uint32_t)((it / stages) & 1);
+            mbar_wait(&full[s], ph);
+            double* T = tiles + (size_t)s * stage_doubles;
+            const long long r0 = t * kTileRows;
+            if (MODE != MODE_COEFF) {
+                // ---- Y = X - Q*C : thread (row, half) owns CW/2 columns of one row
+                constexpr int HC = CW / 2;
+                const int row = tid & (kTileRows - 1), half = tid >> 7;
+                double y[HC];
+#pragma unroll
+                for (int j = 0; j < HC; ++j) y[j] = T[(size_t)(8 * MT + half * HC + j) * kPitch + row];
+                for (int m = 0; m < p.M; ++m) {
+                    const double q = T[(size_t)m * kPitch + row];
+#pragma unroll
+                    for (int j = 0; j < HC; ++j) y[j] = fma(-q, Cs[m * CW + half * HC + j], y[j]);
+                }
+                const bool ok = r0 + row < p.n;
+#pragma unroll
+                for (int j = 0; j < HC; ++j) {
+                    const int col = half * HC + j;
+                    T[(size_t)(8 * MT + col) * kPitch + row] = y[j];
+                    if (ok && col < p.c) p.Y[(long long)col * p.ldY + r0 + row] = y[j];
+                }
+                consumer_sync();                 // the whole Y tile is in shared memory before anyone contracts it
+            }
+            // ---- contraction over the 16 rows of this warp: S += [Q Y]' Y
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int row = 16 * warp + 4 * u + tq;
+                double bf[CT], af[NRT];
+#pragma unroll
+                for (int b = 0; b < CT; ++b) bf[b] = T[(size_t)(8 * MT + 8 * b + g) * kPitch + row];
+#pragma unroll
+                for (int a = 0; a < NRT; ++a) {
+                    const int rt = RT0 + a;
+                    af[a] = (rt >= MT) ? bf[rt - MT] : T[(size_t)(8 * rt + g) * kPitch + row];
+                }
+#pragma unroll
+                for (int a = 0; a < NRT; ++a)
+#pragma unroll
+                    for (int b = 0; b < CT; ++b) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+            }
+            if (MODE != MODE_COEFF) fence_proxy_async();      // our generic-proxy writes vs the next TMA refill of this stage
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        // ---- CTA reduction over the consumer warps (fixed order)
+        double* mine = red + (size_t)warp * NRT * CT * 64;
+#pragma unroll
+        for (int a = 0; a < NRT; ++a)
+#pragma unroll
+            for (int b = 0; b < CT; ++b) {
+                double* tile = mine + (a * CT + b) * 64;
+                tile[g * 8 + 2 * tq] = acc[a][b][0];
+                tile[g * 8 + 2 * tq + 1] = acc[a][b][1];
+            }
+    }
+    __syncthreads();
+    constexpr int ELEMS = NRT * CT * 64;
+    double* out = p.partials + (size_t)blockIdx.x * ELEMS;
+    for (int e = tid; e < ELEMS; e += kTileThreads) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < kConsumerWarps; ++w) sum += red[(size_t)w * ELEMS + e];
+        out[e] = sum;
+    }
+    __threadfence();
+    __shared__ bool is_last;
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int e = warp; e < ELEMS; e += kConsumerWarps + 1) {
+        const int tl = e >> 6, i = (e >> 3) & 7, j = e & 7;
+        const int rt = RT0 + tl / CT, ct = tl % CT;
+        const int col = 8 * ct + j;
+        int rowS;                                          // row of S: Q-part first, block-part after it
+        bool valid;
+        if (rt < MT) { rowS = 8 * rt + i; valid = rowS < p.M; }
+        else { const int k = 8 * (rt - MT) + i; rowS = p.M + k; valid = k < p.c; }
+        if (!valid || col >= p.c) continue;
+        double sum = 0.0;
+        for (unsigned int b0 = lane; b0 < gridDim.x; b0 += 256) {
+            double v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const unsigned int b = b0 + 32 * q;
+                v[q] = b < gridDim.x ? __ldcg(p.partials + (size_t)b * ELEMS + e) : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sum += v[q];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) p.S[(size_t)col * p.ldS + rowS] = sum;
+    }
+    if (tid == 0) *p.ticket = 0;
+}
+
+template <int MT, int CT, int MODE>
+int launch_tile(calz_ctx* ctx, const TileArgs& a0) {
+    TileArgs a = a0;
+    constexpr int SLOTS = 8 * (MT + CT);
+    constexpr int NRT = (MODE == MODE_UPDATE_GRAM) ? CT : MT + CT;
+    const size_t stage_bytes = (size_t)SLOTS * kPitch * sizeof(double);
+    const size_t fixed = ((size_t)MT * 8 * 8 * CT + (size_t)kConsumerWarps * NRT * CT * 64) * sizeof(double) + 2 * 8 * sizeof(uint64_t) + 64;
+    int dev_max = 0;
+    cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+    int stages = 4;
+    while (stages > 2 && fixed + stages * stage_bytes > (size_t)dev_max / 2 - 1024) --stages;     // aim for 2 CTAs per SM
+    const size_t smem = fixed + stages * stage_bytes;
+    if (smem > (size_t)dev_max) return set_error(ctx, CALZ_ERR_UNSUPPORTED, "tile kernel needs %zu B of shared memory", smem);
+    auto kern = k_tile<MT, CT, MODE>;
+    CALZ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTileThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    per_sm = std::min(per_sm, 2);
+    const long long ntiles = (a.n + kTileRows - 1) / kTileRows;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((long long)ctx->num_sms * per_sm, ntiles));
+    CALZ_TRY(reserve(ctx, ctx->partials, (size_t)grid * NRT * CT * 64 * sizeof(double)));
+    a.partials = (double*)ctx->partials.p;
+    a.ticket = ctx->ticket;
+    kern<<<grid, kTileThreads, smem, ctx->stream>>>(a, stages);
+    CALZ_LAUNCH_CHECK(ctx);
+    return CALZ_OK;
+}
+
+bool aligned16(const void* p, long long ld) { return ((uintptr_t)p % 16 == 0) && (ld % 2 == 0); }
+
+}  // namespace
+
+bool tile_path_ok(int64_t n, const double* Q, int64_t ldQ, int M, const double* X, int64_t ldX, int c, const double* Y, int64_t ldY) {
+    return n >= kTileRows && M >= 1 && M <= 16 && c >= 1 && c <= 16 && aligned16(Q, ldQ) && aligned16(X, ldX) && (!Y || aligned16(Y, ldY));
+}
+
+// mode: 0 = COEFF (S = [Q X]'X), 1 = UPDATE_FULL (Y = X - Q*C, S = [Q Y]'Y), 2 = UPDATE_GRAM (Y = X - Q*C, S rows [M,M+c) = Y'Y)
+int tile_pass(calz_ctx* ctx, int mode, int64_t n, const double* Q, int64_t ldQ, int M, const double* X, int64_t ldX, int c,
+              const double* C_dev, int ldC, double* Y, int64_t ldY, double* S_dev, int ldS, const int* pred, int want, bool allreduce) {
+    TileArgs a{};
+    a.n = n; a.Q = Q; a.ldQ = ldQ; a.M = M; a.X = X; a.ldX = ldX; a.c = c; a.Y = Y; a.ldY = ldY; a.C = C_dev; a.ldC = ldC;
+    a.S = S_dev; a.ldS = ldS; a.pred = pred; a.want = want;
+    const int MT = (M + 7) / 8, CT = (c + 7) / 8;
+    int st;
+#define CALZ_TILE(MTv, CTv)                                                         \
+    st = mode == 0 ? launch_tile<MTv, CTv, MODE_COEFF>(ctx, a)                      \
+       : mode == 1 ? launch_tile<MTv, CTv, MODE_UPDATE_FULL>(ctx, a)                \
+                   : launch_tile<MTv, CTv, MODE_UPDATE_GRAM>(ctx, a)
+    if (MT == 1 && CT == 1) { CALZ_TILE(1, 1); }
+    else if (MT == 2 && CT == 1) { CALZ_TILE(2, 1); }
+    else if (MT == 1 && CT == 2) { CALZ_TILE(1, 2); }
+    else { CALZ_TILE(2, 2); }
+#undef CALZ_TILE
+    CALZ_TRY(st);
+    if (allreduce && ctx->nranks > 1) {
+        // a predicated-off pass leaves S untouched on every rank alike, so the collective stays consistent
+        if (mode == 2) {
+            if (ldS != M + c) return set_error(ctx, CALZ_ERR_BADARG, "tile_pass: dense S expected");
+            // only the block-part rows are produced: reduce them column by column would cost c collectives; reduce all
+        }
+        CALZ_TRY(allreduce_sum(ctx, S_dev, (size_t)ldS * c));
+    }
+    return CALZ_OK;
+}
+
+}  // namespace calz

@@ -322,17 +322,17 @@ __device__ void norm_drop_flag(int c, const double (*R)[kMaxC + 1], const double
 // 1 if a shift was needed or min_j R_jj/sqrt(G_jj) < thresh, i.e. one CholQR pass is not Householder-accurate.
 __global__ void k_chol_small(int c, const double* __restrict__ G, double* __restrict__ Rout, int* info_out,
                              const double* __restrict__ nb2, int nb2_stride, int* flag_out,
-                             const int* __restrict__ pred, int want, int adaptive, double thresh, int* cond_out) {
+                             const int* __restrict__ pred, int want, int adaptive, double thresh, int* cond_out, int ldG) {
     if (pred && *pred != want) return;
     __shared__ double A[kMaxC][kMaxC + 1];
     const int lane = threadIdx.x;
-    double gdiag = (lane < c) ? G[(size_t)lane * c + lane] : 0.0, gmax = gdiag;
+    double gdiag = (lane < c) ? G[(size_t)lane * ldG + lane] : 0.0, gmax = gdiag;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
     double shift = 0.0;
     int info = 0, nshift = 0;
     while (true) {
-        for (int e = lane; e < c * c; e += 32) A[e % c][e / c] = G[e] + ((e % c == e / c) ? shift : 0.0);     // A[i][j] = G(i,j)
+        for (int e = lane; e < c * c; e += 32) A[e % c][e / c] = G[(size_t)(e / c) * ldG + e % c] + ((e % c == e / c) ? shift : 0.0);     // A[i][j] = G(i,j)
         __syncwarp();
         info = 0;
         // right-looking upper Cholesky, lane l owns column l
@@ -373,10 +373,10 @@ __global__ void k_chol_small(int c, const double* __restrict__ G, double* __rest
 }
 
 int chol_small(calz_ctx* ctx, int c, const double* G_dev, double* R_dev, int* info_out, const double* nb2,
-               int nb2_stride, int* flag_out, const int* pred, int want, bool adaptive, int* cond_out) {
+               int nb2_stride, int* flag_out, const int* pred, int want, bool adaptive, int* cond_out, int ldG) {
     if (c > kMaxC) return set_error(ctx, CALZ_ERR_UNSUPPORTED, "block width c=%d > %d", c, kMaxC);
     k_chol_small<<<1, 32, 0, ctx->stream>>>(c, G_dev, R_dev, info_out, nb2, nb2_stride, nb2 ? flag_out : nullptr, pred, want,
-                                            adaptive ? 1 : 0, 1.0 / (double)ctx->opt_cholqr2_inv_thresh, cond_out);
+                                            adaptive ? 1 : 0, 1.0 / (double)ctx->opt_cholqr2_inv_thresh, cond_out, ldG > 0 ? ldG : c);
     CALZ_LAUNCH_CHECK(ctx);
     return CALZ_OK;
 }

@@ -47,7 +47,13 @@ int rmul_upper(calz_ctx* ctx, int c, const double* Rb, double* Rfin, const int* 
 // *flag_out = max_i |sqrt(nb2[i*nb2_stride]) - ||R(:,i)|| | / sqrt(nb2[...]) > 0.5.  info_out: 0 or failing pivot.
 // adaptive (CALZ_QR_CHOLQR2): shifted retry on breakdown (info_out = -#shifts), cond_out = "needs another CholQR pass".
 int chol_small(calz_ctx* ctx, int c, const double* G_dev, double* R_dev, int* info_out, const double* nb2,
-               int nb2_stride, int* flag_out, const int* pred, int want, bool adaptive = false, int* cond_out = nullptr);
+               int nb2_stride, int* flag_out, const int* pred, int want, bool adaptive = false, int* cond_out = nullptr,
+               int ldG = 0);
+
+// fused TMA-tile passes of projectAndNormalize (tiles.cu)
+bool tile_path_ok(int64_t n, const double* Q, int64_t ldQ, int M, const double* X, int64_t ldX, int c, const double* Y, int64_t ldY);
+int tile_pass(calz_ctx* ctx, int mode, int64_t n, const double* Q, int64_t ldQ, int M, const double* X, int64_t ldX, int c,
+              const double* C_dev, int ldC, double* Y, int64_t ldY, double* S_dev, int ldS, const int* pred, int want, bool allreduce);
 
 // same decision for a backend that already has R on the device (TSQR)
 int norm_drop_decision(calz_ctx* ctx, int c, const double* R_dev, const double* nb2, int nb2_stride, int* flag_out);
