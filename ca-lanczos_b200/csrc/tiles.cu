@@ -159,6 +159,7 @@ k_tile(TileArgs p, int stages) {
                 double y[HC];
 #pragma unroll
                 for (int j = 0; j < HC; ++j) y[j] = T[(size_t)(8 * MT + half * HC + j) * kPitch + row];
+#pragma unroll 3
                 for (int m = 0; m < p.M; ++m) {
                     const double q = T[(size_t)m * kPitch + row];
 #pragma unroll
@@ -257,8 +258,12 @@ int launch_tile(calz_ctx* ctx, const TileArgs& a0) {
     const size_t fixed = ((size_t)MT * 8 * 8 * CT + (size_t)kConsumerWarps * NRT * CT * 64) * sizeof(double) + 2 * 8 * sizeof(uint64_t) + 64;
     int dev_max = 0;
     cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
+    // aim for 2 CTAs per SM: 228 KB per SM minus 1 KB the driver reserves per resident CTA
+    int sm_max = 0;
+    cudaDeviceGetAttribute(&sm_max, cudaDevAttrMaxSharedMemoryPerMultiprocessor, ctx->device);
+    const size_t budget = ((size_t)sm_max - 2 * 1024) / 2 - 512;
     int stages = 4;
-    while (stages > 2 && fixed + stages * stage_bytes > (size_t)dev_max / 2 - 1024) --stages;     // aim for 2 CTAs per SM
+    while (stages > 2 && fixed + stages * stage_bytes > budget) --stages;
     const size_t smem = fixed + stages * stage_bytes;
     if (smem > (size_t)dev_max) return set_error(ctx, CALZ_ERR_UNSUPPORTED, "tile kernel needs %zu B of shared memory", smem);
     auto kern = k_tile<MT, CT, MODE>;
