@@ -60,6 +60,9 @@ SIGNATURES = {
     "calz_project": (C.c_int, [c_vp, c_i64, C.c_int, C.POINTER(c_vp), c_i64p, c_ip, C.c_int, c_vp, c_i64, C.c_int, C.POINTER(c_dp)]),
     "calz_project_and_normalize": (C.c_int, [c_vp, c_i64, C.c_int, C.POINTER(c_vp), c_i64p, c_ip, C.c_int, c_vp, c_i64,
                                              C.c_int, C.c_int, c_vp, c_i64, C.POINTER(c_dp), c_dp, c_ip, c_ip]),
+    "calz_project_and_normalize_async": (C.c_int, [c_vp, c_i64, C.c_int, C.POINTER(c_vp), c_i64p, c_ip, C.c_int, c_vp, c_i64,
+                                                   C.c_int, C.c_int, c_vp, c_i64, c_ip]),
+    "calz_pan_collect": (C.c_int, [c_vp, C.c_int, C.POINTER(c_dp), c_dp, c_ip, c_ip, c_ip]),
     "calz_tsqr_host": (C.c_int, [c_vp, c_i64, C.c_int, c_dp, c_i64, c_dp, c_i64, c_dp]),
     "calz_cholqr_host": (C.c_int, [c_vp, c_i64, C.c_int, c_dp, c_i64, c_dp, c_i64, c_dp, c_ip]),
     "calz_normalize_host": (C.c_int, [c_vp, c_i64, C.c_int, c_dp, c_i64, C.c_int, C.c_double, c_dp, c_i64, c_dp, c_ip]),

@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 
 #include "tsops.cuh"
 
@@ -202,9 +203,27 @@ int calz_project(calz_ctx* ctx, int64_t n, int nblk, const double* const* Qblk, 
     return CALZ_OK;
 }
 
-int calz_project_and_normalize(calz_ctx* ctx, int64_t n, int nblk, const double* const* Qblk, const int64_t* ldQ,
-                               const int* mcols, int c, const double* X, int64_t ldX, int doreorth, int backend,
-                               double* QZ, int64_t ldQZ, double* const* Rblk, double* Rlast, int* second_pass, int* rank) {
+// ---- one projectAndNormalize call in flight: where its small results live and how to unpack them
+struct PanSlot {
+    bool busy = false;
+    cudaEvent_t ev = nullptr;
+    double* host = nullptr;          // pinned
+    size_t host_doubles = 0;
+    int nb = 0, c = 0, backend = 0, nblk = 0;
+    int64_t n = 0, ldQZ = 0;
+    double* QZ = nullptr;
+    double* sm = nullptr;            // device scratch base (valid until the next call on the stream reuses it)
+    std::vector<int> blocks, mc, ld1, ld2;
+    std::vector<size_t> off1, off2;
+    size_t offRf = 0, offG2 = 0, doubles = 0;
+};
+constexpr int kPanSlots = 8;
+struct PanRing { PanSlot slot[kPanSlots]; int next = 0; };
+static std::map<calz_ctx*, PanRing*> g_rings;
+
+static int pan_enqueue(calz_ctx* ctx, int64_t n, int nblk, const double* const* Qblk, const int64_t* ldQ,
+                       const int* mcols, int c, const double* X, int64_t ldX, int doreorth, int backend,
+                       double* QZ, int64_t ldQZ, PanSlot& slot) {
     if (!ctx || !X || !QZ || n < 1 || c < 1 || c > kMaxC || nblk < 0 ||
         (backend != CALZ_QR_TSQR && backend != CALZ_QR_CHOLQR && backend != CALZ_QR_CHOLQR2))
         return set_error(ctx, CALZ_ERR_BADARG, "calz_project_and_normalize: bad arguments");
@@ -305,37 +324,98 @@ int calz_project_and_normalize(calz_ctx* ctx, int64_t n, int nblk, const double*
         CALZ_TRY(tsqr_form_q(ctx, n, c, src, ldsrc, QZ, ldQZ));
     }
 
-    // ---- small results: one D2H copy, one synchronisation
-    CALZ_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, sm, doubles * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const double* h = ctx->pinned;
+    // ---- small results: one D2H copy into this call's pinned slot, completion event
+    if (slot.host_doubles < doubles) {
+        if (slot.host) cudaFreeHost(slot.host);
+        slot.host_doubles = std::max<size_t>(doubles * 2, 4096);
+        CALZ_CUDA(ctx, cudaMallocHost(&slot.host, slot.host_doubles * sizeof(double)));
+    }
+    if (!slot.ev) CALZ_CUDA(ctx, cudaEventCreateWithFlags(&slot.ev, cudaEventDisableTiming));
+    CALZ_CUDA(ctx, cudaMemcpyAsync(slot.host, sm, doubles * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CALZ_CUDA(ctx, cudaEventRecord(slot.ev, ctx->stream));
+    slot.busy = true;
+    slot.nb = nb; slot.c = c; slot.backend = backend; slot.nblk = nblk; slot.n = n; slot.QZ = QZ; slot.ldQZ = ldQZ; slot.sm = sm;
+    slot.blocks = blocks; slot.ld1 = ld1; slot.ld2 = ld2; slot.off1 = off1; slot.off2 = off2;
+    slot.mc.assign(nblk, 0);
+    for (int i = 0; i < nblk; ++i) slot.mc[i] = empty_block(Qblk, mcols, i) ? 0 : mcols[i];
+    slot.offRf = offRf; slot.offG2 = offG2; slot.doubles = doubles;
+    return CALZ_OK;
+}
+
+// wait for the call, unpack the small results; allow_refine: run the (rare) CholQR2 refinement passes here
+static int pan_finish(calz_ctx* ctx, PanSlot& slot, double* const* Rblk, double* Rlast, int* second_pass, int* rank,
+                      bool allow_refine, int* needs_refine) {
+    if (!slot.busy) return set_error(ctx, CALZ_ERR_BADARG, "projectAndNormalize: nothing to collect");
+    CALZ_CUDA(ctx, cudaEventSynchronize(slot.ev));
+    slot.busy = false;
+    const int c = slot.c, nb = slot.nb, backend = slot.backend;
+    const double* h = slot.host;
     const int* hf = (const int*)h;
     const bool second = hf[0] != 0;
     int info = second ? hf[2] : hf[1];
     if (info < 0) info = 0;                                              // negative = shifted retries (CholQR2), not a failure
+    if (needs_refine) *needs_refine = 0;
     if (!info && backend == CALZ_QR_CHOLQR2 && hf[5]) {
         // rare path: the conditioning estimate asks for re-orthogonalisation (first block of an ill-conditioned start)
-        CALZ_TRY(cholqr_refine(ctx, n, c, QZ, ldQZ, Rf, sm + offG2, flags + 6, &info));
-        CALZ_CUDA(ctx, cudaMemcpyAsync(ctx->pinned + offRf, Rf, (size_t)c * c * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-        CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (!allow_refine) {
+            if (needs_refine) *needs_refine = 1;
+        } else {
+            double* Rf = slot.sm + slot.offRf;
+            CALZ_TRY(cholqr_refine(ctx, slot.n, c, slot.QZ, slot.ldQZ, Rf, slot.sm + slot.offG2, (int*)slot.sm + 6, &info));
+            CALZ_CUDA(ctx, cudaMemcpyAsync(slot.host + slot.offRf, Rf, (size_t)c * c * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
     }
     if (second_pass) *second_pass = second ? 1 : 0;
     for (int k = 0; k < nb; ++k) {
-        const int i = blocks[k], m = mcols[i];
+        const int i = slot.blocks[k], m = slot.mc[i];
         if (!Rblk || !Rblk[i]) continue;
         for (int j = 0; j < c; ++j)
             for (int a = 0; a < m; ++a) {
-                double v = h[off1[k] + (size_t)j * ld1[k] + a];
-                if (second) v = h[off2[k] + (size_t)j * ld2[k] + a] + v;      // RZ{i} = RZ{i} + RY{i}  (:71-73)
+                double v = h[slot.off1[k] + (size_t)j * slot.ld1[k] + a];
+                if (second) v = h[slot.off2[k] + (size_t)j * slot.ld2[k] + a] + v;      // RZ{i} = RZ{i} + RY{i}  (:71-73)
                 Rblk[i][(size_t)j * m + a] = v;
             }
     }
-    const double* Rl = h + offRf;
+    const double* Rl = h + slot.offRf;
     if (Rlast) memcpy(Rlast, Rl, (size_t)c * c * sizeof(double));
     if (rank) *rank = numerical_rank(c, Rl, c, 1.0e-8);
     if (info) return set_error(ctx, CALZ_ERR_CHOL, "projectAndNormalize/cholqr: Gram matrix not positive definite at pivot %d (pass %d)",
                                info, second ? 2 : 1);
     return CALZ_OK;
+}
+
+static PanRing* ring_of(calz_ctx* ctx) {
+    PanRing*& r = g_rings[ctx];
+    if (!r) r = new PanRing();
+    return r;
+}
+
+int calz_project_and_normalize(calz_ctx* ctx, int64_t n, int nblk, const double* const* Qblk, const int64_t* ldQ,
+                               const int* mcols, int c, const double* X, int64_t ldX, int doreorth, int backend,
+                               double* QZ, int64_t ldQZ, double* const* Rblk, double* Rlast, int* second_pass, int* rank) {
+    int ticket = -1;
+    CALZ_TRY(calz_project_and_normalize_async(ctx, n, nblk, Qblk, ldQ, mcols, c, X, ldX, doreorth, backend, QZ, ldQZ, &ticket));
+    return pan_finish(ctx, ring_of(ctx)->slot[ticket], Rblk, Rlast, second_pass, rank, true, nullptr);
+}
+
+int calz_project_and_normalize_async(calz_ctx* ctx, int64_t n, int nblk, const double* const* Qblk, const int64_t* ldQ,
+                                     const int* mcols, int c, const double* X, int64_t ldX, int doreorth, int backend,
+                                     double* QZ, int64_t ldQZ, int* ticket) {
+    if (!ctx || !ticket) return set_error(ctx, CALZ_ERR_BADARG, "calz_project_and_normalize_async: bad arguments");
+    PanRing* ring = ring_of(ctx);
+    const int t = ring->next;
+    if (ring->slot[t].busy)
+        return set_error(ctx, CALZ_ERR_BADARG, "projectAndNormalize: %d calls in flight, collect some first", kPanSlots);
+    CALZ_TRY(pan_enqueue(ctx, n, nblk, Qblk, ldQ, mcols, c, X, ldX, doreorth, backend, QZ, ldQZ, ring->slot[t]));
+    ring->next = (t + 1) % kPanSlots;
+    *ticket = t;
+    return CALZ_OK;
+}
+
+int calz_pan_collect(calz_ctx* ctx, int ticket, double* const* Rblk, double* Rlast, int* second_pass, int* rank, int* needs_refine) {
+    if (!ctx || ticket < 0 || ticket >= kPanSlots) return set_error(ctx, CALZ_ERR_BADARG, "calz_pan_collect: bad ticket");
+    return pan_finish(ctx, ring_of(ctx)->slot[ticket], Rblk, Rlast, second_pass, rank, false, needs_refine);
 }
 
 // ------------------------------------------------------------------------------------------ host flavours

@@ -57,6 +57,8 @@ class BlockEngine:
         self.Q = torch.zeros((self.max_cols, self.ld), dtype=torch.float64, device=dev)
         torch.cuda.synchronize(dev)          # libcalz runs on its own stream
         self.k = 0
+        self.k_enq = 0
+        self.pending = []
         self.T = None
         self.b = np.zeros(int(max_blocks) + 2)
         self.second = []
@@ -124,6 +126,55 @@ class BlockEngine:
         if assemble_T:
             self._extend_T(k, self._R1, self._Rl)
         return bool(second.value)
+
+    # ---- asynchronous pipeline: the GPU never waits for the host's O(s^3) algebra or for result read-back
+    def _enqueue_block(self):
+        s = self.s
+        k = self.k_enq + 1
+        if k * s + 1 > self.max_cols:
+            raise RuntimeError("BlockEngine: Q storage exhausted")
+        V, ldV = self._mpk(self._qcol((k - 1) * s))
+        qblk = (C.c_void_p * 1)(self._qcol((k - 2) * s))
+        lds = (C.c_int64 * 1)(self.ld)
+        mc = (C.c_int * 1)(s + 1)
+        ticket = C.c_int(-1)
+        check(self.lib.calz_project_and_normalize_async(self.ctx.h, self.n, 1, qblk, lds, mc, s, C.c_void_p(V + 8 * ldV), ldV, 1,
+                                                        _lib.QR[self.backend], C.c_void_p(self._qcol((k - 1) * s + 1)), self.ld,
+                                                        C.byref(ticket)), self.ctx.h)
+        self.k_enq = k
+        self.pending.append((k, int(ticket.value)))
+
+    def _collect_one(self, assemble_T=True):
+        k, ticket = self.pending.pop(0)
+        rp = (_lib.c_dp * 1)(self._R1.ctypes.data_as(_lib.c_dp))
+        second, rank, refine = C.c_int(), C.c_int(), C.c_int()
+        check(self.lib.calz_pan_collect(self.ctx.h, ticket, rp, self._Rl.ctypes.data_as(_lib.c_dp), C.byref(second), C.byref(rank),
+                                        C.byref(refine)), self.ctx.h)
+        if refine.value:
+            # CholQR2 asked for a refinement pass on this block: everything enqueued after it used an unrefined Q.
+            # Roll back and redo this block synchronously (rare: ill-conditioned basis blocks only).
+            for _, t in self.pending:
+                self.lib.calz_pan_collect(self.ctx.h, t, None, None, None, None, None)
+            self.pending = []
+            self.ctx.sync()
+            self.k = k - 1
+            self.next_block(assemble_T)
+            self.k_enq = self.k
+            return
+        self.k = k
+        self.second.append(bool(second.value))
+        if assemble_T:
+            self._extend_T(k, self._R1, self._Rl)
+
+    def run_blocks(self, nblocks: int, lag: int = 3, assemble_T: bool = True):
+        """Advance by ``nblocks`` outer iterations with up to ``lag`` projectAndNormalize calls in flight."""
+        self.k_enq = self.k
+        self.pending = []
+        target = self.k + int(nblocks)
+        while self.k < target:
+            while self.k_enq < target and len(self.pending) < lag:
+                self._enqueue_block()
+            self._collect_one(assemble_T)
 
     def _extend_T(self, k, Rkk_s, Rk_s):
         """ca_lanczos.m:200-223."""

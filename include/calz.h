@@ -149,6 +149,14 @@ int  calz_project_and_normalize(calz_ctx* ctx, int64_t n, int nblk, const double
                                 const int64_t* ldQ, const int* mcols, int c, const double* X, int64_t ldX,
                                 int doreorth, int backend, double* QZ, int64_t ldQZ, double* const* Rblk,
                                 double* Rlast, int* second_pass, int* rank);
+/* Asynchronous variant for the device-resident pipeline: enqueues the whole call and returns a ticket at once (up
+ * to 8 calls in flight); calz_pan_collect waits for that call only and unpacks its small results.  The rare CholQR2
+ * refinement cannot run behind the caller's back: *needs_refine=1 tells the caller to redo that block synchronously. */
+int  calz_project_and_normalize_async(calz_ctx* ctx, int64_t n, int nblk, const double* const* Qblk,
+                                      const int64_t* ldQ, const int* mcols, int c, const double* X, int64_t ldX,
+                                      int doreorth, int backend, double* QZ, int64_t ldQZ, int* ticket);
+int  calz_pan_collect(calz_ctx* ctx, int ticket, double* const* Rblk, double* Rlast, int* second_pass, int* rank,
+                      int* needs_refine);
 /* host-pointer flavours (synchronous) */
 int  calz_tsqr_host(calz_ctx* ctx, int64_t n, int c, const double* A, int64_t ldA, double* Q, int64_t ldQ, double* R);
 int  calz_cholqr_host(calz_ctx* ctx, int64_t n, int c, const double* X, int64_t ldX, double* Q, int64_t ldQ,
