@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--m", type=int, default=256, help="grid edge (256 = the BASELINE workload)")
+    ap.add_argument("--mz", type=int, default=0, help="z extent (default m): --mz 32 is the per-rank share of the 8-GPU run")
     ap.add_argument("--s", type=int, default=8)
     ap.add_argument("--backend", default="cholqr2", choices=["cholqr", "cholqr2", "tsqr"])
     ap.add_argument("--layout", default="sell", choices=["sell", "csr", "auto"])
@@ -208,19 +209,20 @@ def run_b200(args):
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     m, s = args.m, args.s
-    n = m * m * m
+    mz = args.mz or m
+    n = m * m * mz
     plane = m * m
-    nnz = 7 * n - 6 * plane
+    nnz = 7 * n - 2 * plane - 4 * m * mz
     lo, hi = (rank * n) // world, ((rank + 1) * n) // world
     have_lo, have_hi = max(0, lo - s * plane), min(n, hi + s * plane)
     t0 = time.time()
-    A = gallery.laplace3d(m, row_lo=have_lo, row_hi=have_hi)
+    A = gallery.laplace3d(m, m, mz, row_lo=have_lo, row_hi=have_hi)
     dm = api.DeviceMatrix(A, s_max=s, layout=args.layout, ctx=ctx, n_glob=n, row_begin=have_lo)
     del A
     setup_s = time.time() - t0
     shifts = gallery.leja_points(0.0, 12.0, s)
     K, W = args.steps, args.warmup
-    eng = BlockEngine(dm, s, K + W + 8, "newton", shifts, args.backend)
+    eng = BlockEngine(dm, s, K + W + 10, "newton", shifts, args.backend)
     n_own = dm.n
     q0 = np.full(n_own, 1.0 / np.sqrt(n))                       # r = ones(n,1), normalised (ca_lanczos.m:55)
     eng.first_block(q0)
@@ -243,13 +245,16 @@ def run_b200(args):
     if sampler:
         sampler.mark()
     ctx.launch_count(reset=True)
+    host_enqueue_ms = None
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e_start.record(stream)
     if args.sync_blocks:
         for i in range(K):
             eng.next_block(events=(ev[i], stream))
     else:
+        eng.host_enqueue_s = 0.0
         eng.run_blocks(K, lag=args.lag)          # results of up to `lag` blocks in flight; returns when T holds all K blocks
+        host_enqueue_ms = 1e3 * eng.host_enqueue_s / K
     e_stop.record(stream)
     e_stop.synchronize()
     barrier()
@@ -259,6 +264,8 @@ def run_b200(args):
     if not args.sync_blocks:
         # per-phase split from a second, synchronous pass over a few blocks (not part of `value`)
         kk = min(K, 5)
+        eng.next_block()
+        barrier()
         for i in range(kk):
             eng.next_block(events=(ev[i], stream))
         ctx.sync()
@@ -306,7 +313,8 @@ def run_b200(args):
         "config": {"workload": workload_name(m, s, args.backend), "n": n, "nnz": nnz, "s": s, "basis": "newton", "orth": args.backend,
                    "layout": dm.layout, "partition": "rows/%d" % world, "l2": "inputs larger than L2 (A %.2f GB, basis %.2f GB per rank)" %
                    (12 * nnz_loc / 1e9, 8 * n_loc * (s + 1) / 1e9), "l2_chunk_mb": args.l2_chunk_mb, "setup_s": round(setup_s, 1)},
-        "phases_ms": {"mpk": ms_mpk, "project_and_normalize": ms_orth, "mpk_share": ms_mpk / (ms_mpk + ms_orth)},
+        "phases_ms": {"mpk": ms_mpk, "project_and_normalize": ms_orth, "mpk_share": ms_mpk / (ms_mpk + ms_orth),
+                      "host_enqueue_ms_per_block": host_enqueue_ms},
         "roofline": {"kernel": "k_spmv_sell (one SpMV step of the MPK)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": spmv_bytes, "launch_ms": launch_ms},

@@ -215,38 +215,44 @@ k_tile(TileArgs p, int stages) {
         for (int w = 0; w < kConsumerWarps; ++w) sum += red[(size_t)w * ELEMS + e];
         out[e] = sum;
     }
-    __threadfence();
-    __shared__ bool is_last;
-    __syncthreads();
-    if (tid == 0) is_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    for (int e = warp; e < ELEMS; e += kConsumerWarps + 1) {
-        const int tl = e >> 6, i = (e >> 3) & 7, j = e & 7;
-        const int rt = RT0 + tl / CT, ct = tl % CT;
-        const int col = 8 * ct + j;
-        int rowS;                                          // row of S: Q-part first, block-part after it
-        bool valid;
-        if (rt < MT) { rowS = 8 * rt + i; valid = rowS < p.M; }
-        else { const int k = 8 * (rt - MT) + i; rowS = p.M + k; valid = k < p.c; }
-        if (!valid || col >= p.c) continue;
-        double sum = 0.0;
-        for (unsigned int b0 = lane; b0 < gridDim.x; b0 += 256) {
-            double v[8];
+}
+
+// Deterministic second stage of the reduction: one warp per element of S sums the per-CTA partials in a fixed order
+// (lanes stride over the CTAs with all loads in flight at once, fixed shuffle tree).  A separate small launch on purpose:
+// done by the last CTA of k_tile it cost ~30 us of serialised L2 latency per pass.
+template <int MT, int CT, int MODE>
+__global__ void __launch_bounds__(256)
+k_tile_finalize(const double* __restrict__ partials, int nparts, double* __restrict__ S, int ldS, int M, int c,
+                const int* __restrict__ pred, int want) {
+    if (pred && *pred != want) return;
+    constexpr int RT0 = (MODE == MODE_UPDATE_GRAM) ? MT : 0;
+    constexpr int NRT = MT + CT - RT0;
+    constexpr int ELEMS = NRT * CT * 64;
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (e >= ELEMS) return;
+    const int tl = e >> 6, i = (e >> 3) & 7, j = e & 7;
+    const int rt = RT0 + tl / CT, ct = tl % CT;
+    const int col = 8 * ct + j;
+    int rowS;                                          // row of S: Q-part first, block-part after it
+    bool valid;
+    if (rt < MT) { rowS = 8 * rt + i; valid = rowS < M; }
+    else { const int k = 8 * (rt - MT) + i; rowS = M + k; valid = k < c; }
+    if (!valid || col >= c) return;
+    double sum = 0.0;
+    for (int b0 = lane; b0 < nparts; b0 += 32 * 16) {
+        double v[16];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const unsigned int b = b0 + 32 * q;
-                v[q] = b < gridDim.x ? __ldcg(p.partials + (size_t)b * ELEMS + e) : 0.0;
-            }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) sum += v[q];
+        for (int q = 0; q < 16; ++q) {
+            const int b = b0 + 32 * q;
+            v[q] = b < nparts ? partials[(size_t)b * ELEMS + e] : 0.0;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        if (lane == 0) p.S[(size_t)col * p.ldS + rowS] = sum;
+        for (int q = 0; q < 16; ++q) sum += v[q];
     }
-    if (tid == 0) *p.ticket = 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) S[(size_t)col * ldS + rowS] = sum;
 }
 
 template <int MT, int CT, int MODE>
@@ -277,6 +283,8 @@ int launch_tile(calz_ctx* ctx, const TileArgs& a0) {
     a.partials = (double*)ctx->partials.p;
     a.ticket = ctx->ticket;
     kern<<<grid, kTileThreads, smem, ctx->stream>>>(a, stages);
+    CALZ_LAUNCH_CHECK(ctx);
+    k_tile_finalize<MT, CT, MODE><<<(NRT * CT * 64 + 7) / 8, 256, 0, ctx->stream>>>(a.partials, grid, a.S, a.ldS, a.M, a.c, a.pred, a.want);
     CALZ_LAUNCH_CHECK(ctx);
     return CALZ_OK;
 }

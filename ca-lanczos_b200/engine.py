@@ -58,6 +58,7 @@ class BlockEngine:
         torch.cuda.synchronize(dev)          # libcalz runs on its own stream
         self.k = 0
         self.k_enq = 0
+        self.host_enqueue_s = 0.0          # host time spent enqueueing blocks (pipelined mode)
         self.pending = []
         self.T = None
         self.b = np.zeros(int(max_blocks) + 2)
@@ -129,6 +130,8 @@ class BlockEngine:
 
     # ---- asynchronous pipeline: the GPU never waits for the host's O(s^3) algebra or for result read-back
     def _enqueue_block(self):
+        import time as _time
+        _t0 = _time.perf_counter()
         s = self.s
         k = self.k_enq + 1
         if k * s + 1 > self.max_cols:
@@ -143,6 +146,7 @@ class BlockEngine:
                                                         C.byref(ticket)), self.ctx.h)
         self.k_enq = k
         self.pending.append((k, int(ticket.value)))
+        self.host_enqueue_s += _time.perf_counter() - _t0
 
     def _collect_one(self, assemble_T=True):
         k, ticket = self.pending.pop(0)
