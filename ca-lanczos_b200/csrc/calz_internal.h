@@ -40,6 +40,27 @@ struct DevBuf {                      // grow-only device scratch
     size_t bytes = 0;
 };
 
+// ---------------------------------------------------------------------------------------------------
+// peer-memory collectives (p2p.cu)
+constexpr int kMaxPeers = 8;
+constexpr int kMboxBufs = 4;             // mailbox generations (2 would do, see p2p.cu)
+constexpr int kMboxSlot = 1024;          // doubles per (generation, source rank)
+constexpr int kFlagAllreduce = 0;        // [kMboxBufs][kMaxPeers]
+constexpr int kFlagHaloData = 32;        // [kMaxPeers] sequence number of the last halo pushed BY that peer
+constexpr int kFlagHaloAck = 40;         // [kMaxPeers] sequence number of my last push that peer has consumed
+constexpr int kFlagCount = 64;
+struct P2P {
+    bool enabled = false;
+    void* base = nullptr;                // mailbox + flags, one IPC-exported allocation
+    double* mbox = nullptr;
+    unsigned long long* flags = nullptr;
+    void* peer_base[kMaxPeers] = {};
+    int* err = nullptr;                  // device flag: a bounded spin gave up
+    unsigned int* tickets = nullptr;
+    unsigned long long seq_allreduce = 0, seq_halo = 0;
+    unsigned long long last_push[kMaxPeers] = {};
+};
+
 }  // namespace calz
 
 struct calz_ctx {
@@ -60,6 +81,8 @@ struct calz_ctx {
     int64_t opt_sell_sigma = 0;      // 0: choose
     int64_t opt_csr_lanes = 0;       // 0: choose
     int64_t opt_cholqr2_inv_thresh = 32;
+    int64_t opt_p2p = 1;             // peer-memory all-reduce / halo push instead of NCCL (when IPC works)
+    calz::P2P p2p;
     int64_t opt_tile_pipeline = 1;   // fused TMA-tile passes in projectAndNormalize (0: legacy kernels)
     int64_t opt_grid_mult = 8;       // CTAs per SM for the persistent tall-skinny kernels
 
@@ -112,6 +135,13 @@ static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * 
 
 // in-place sum over ranks of a small device fp64 buffer (no-op without a communicator)
 int allreduce_sum(calz_ctx* ctx, double* dev, size_t count);
+
+// peer-memory collectives (p2p.cu)
+int p2p_setup(calz_ctx* ctx);
+void p2p_teardown(calz_ctx* ctx);
+bool p2p_allreduce_ok(const calz_ctx* ctx, size_t count);
+int p2p_allreduce(calz_ctx* ctx, double* dev, size_t count);
+int p2p_check(calz_ctx* ctx);
 
 // host small algebra (smallalg.cu)
 void svd_singular_values(int c, const double* R, int ldR, double* sigma);   // one-sided Jacobi

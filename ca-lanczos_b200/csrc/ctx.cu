@@ -87,6 +87,7 @@ int nccl_load(const char* path, NcclApi** api, std::string* err) {
 
 int allreduce_sum(calz_ctx* ctx, double* dev, size_t count) {
     if (ctx->nranks <= 1 || count == 0) return CALZ_OK;
+    if (p2p_allreduce_ok(ctx, count)) return p2p_allreduce(ctx, dev, count);
     CALZ_NCCL(ctx, ctx->nccl->AllReduce(dev, dev, count, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
     return CALZ_OK;
 }
@@ -184,6 +185,7 @@ int calz_finalize(calz_ctx* ctx) {
     if (!ctx) return CALZ_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    p2p_teardown(ctx);
     if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
     DevBuf* bufs[] = {&ctx->partials, &ctx->small, &ctx->work[0], &ctx->work[1], &ctx->work[2], &ctx->work[3], &ctx->tsqr_r};
     for (DevBuf* b : bufs)
@@ -214,7 +216,7 @@ void* calz_get_stream(calz_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr
 int calz_sync(calz_ctx* ctx) {
     if (!ctx) return CALZ_ERR_BADARG;
     CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return CALZ_OK;
+    return p2p_check(ctx);
 }
 
 int64_t calz_launch_count(calz_ctx* ctx, int reset) {
@@ -230,6 +232,7 @@ int calz_set_option(calz_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "sell_sigma")) ctx->opt_sell_sigma = value;
     else if (!strcmp(key, "csr_lanes")) ctx->opt_csr_lanes = value;
     else if (!strcmp(key, "cholqr2_inv_thresh")) ctx->opt_cholqr2_inv_thresh = value > 0 ? value : 32;
+    else if (!strcmp(key, "p2p")) ctx->opt_p2p = value;
     else if (!strcmp(key, "tile_pipeline")) ctx->opt_tile_pipeline = value;
     else if (!strcmp(key, "grid_mult")) ctx->opt_grid_mult = value > 0 ? value : 1;
     else return set_error(ctx, CALZ_ERR_BADARG, "calz_set_option: unknown key '%s'", key);
@@ -262,7 +265,7 @@ int calz_comm_init(calz_ctx* ctx, int nranks, int rank, const char id[128], cons
     CALZ_NCCL(ctx, ctx->nccl->CommInitRank(&ctx->comm, nranks, uid, rank));
     ctx->rank = rank;
     ctx->nranks = nranks;
-    return CALZ_OK;
+    return p2p_setup(ctx);        // peer-memory mailbox over CUDA IPC; silently stays on NCCL if IPC is unavailable
 }
 
 int calz_comm_rank(const calz_ctx* ctx, int* rank, int* nranks) {

@@ -89,6 +89,7 @@ int calz_level_sets(int64_t n_glob, int64_t row_begin, int64_t row_end, const in
 int calz_mat_destroy(calz_mat* m) {
     if (!m) return CALZ_OK;
     if (m->ctx) cudaStreamSynchronize(m->ctx->stream);
+    p2p_halo_teardown(m);
     void* ptrs[] = {m->d_send_idx, m->d_send_buf, m->d_rowptr, m->d_colind, m->d_val, m->d_slice_ptr,
                     m->d_sell_col, m->d_sell_val, m->d_perm, m->d_W};
     for (void* p : ptrs)
@@ -399,6 +400,7 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
         return set_error(ctx, CALZ_ERR_ALLOC, "basis workspace %zu bytes: %s", wbytes, cudaGetErrorString(e));
     }
     CALZ_CUDA(ctx, cudaMemset(m->d_W, 0, wbytes));
+    if (P > 1) CALZ_TRY(p2p_halo_setup(m));
     *out = m;
     return CALZ_OK;
 }

@@ -22,6 +22,11 @@ struct calz_mat {
     int32_t* d_send_idx = nullptr;                   // local indices to pack, all peers concatenated
     double* d_send_buf = nullptr;
 
+    // peer-memory halo (p2p.cu): the peers' basis workspaces and where my rows land in them
+    bool p2p_halo = false;
+    std::vector<double*> peer_W;
+    std::vector<long long> peer_dst_off;
+
     // CSR (local indices)
     int32_t* d_rowptr = nullptr;
     int32_t* d_colind = nullptr;
@@ -40,3 +45,10 @@ struct calz_mat {
     double* d_W = nullptr;
     int64_t ldW = 0;
 };
+
+namespace calz {
+int p2p_halo_setup(calz_mat* m);
+void p2p_halo_teardown(calz_mat* m);
+int p2p_halo_exchange(calz_mat* m, double* w);
+int p2p_halo_ack(calz_mat* m);
+}  // namespace calz

@@ -129,6 +129,7 @@ int halo_exchange(calz_mat* m, double* w) {
     calz_ctx* ctx = m->ctx;
     const int P = ctx->nranks;
     if (P <= 1) return CALZ_OK;
+    if (m->p2p_halo) return p2p_halo_exchange(m, w);      // push into the peers' ghost zones over NVLink (p2p.cu)
     for (int q = 0; q < P; ++q)
         if (m->send_cnt[q] && !m->send_contig[q]) {
             const int64_t n = m->send_cnt[q];
@@ -218,6 +219,7 @@ int mpk_run(calz_mat* m, const double* v, int s, const Shifts& sh) {
                 CALZ_TRY(step(k, std::max<int64_t>(lo, 0), std::min<int64_t>(hi, m->n_loc)));
             }
     }
+    if (m->p2p_halo) CALZ_TRY(p2p_halo_ack(m));           // column-0 ghosts consumed: the owners may push the next ones
     return CALZ_OK;
 }
 
