@@ -443,6 +443,8 @@ int calz_mat_info(const calz_mat* m, const char* what, int64_t* value) {
     else if (!strcmp(what, "bandwidth")) *value = m->bandwidth;
     else if (!strcmp(what, "s_max")) *value = m->s_max;
     else if (!strcmp(what, "ldW")) *value = m->ldW;
+    else if (!strcmp(what, "p2p_halo")) *value = m->p2p_halo ? 1 : 0;
+    else if (!strcmp(what, "p2p_allreduce")) *value = (m->ctx && m->ctx->p2p.enabled) ? 1 : 0;
     else return set_error(m->ctx, CALZ_ERR_BADARG, "calz_mat_info: unknown key '%s'", what);
     return CALZ_OK;
 }

@@ -26,5 +26,18 @@ for ss in (1, 2, 4, 8):
     for _ in range(10): f()
     e1.record(stream); e1.synchronize()
     t = torch.tensor([e0.elapsed_time(e1) / 10], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    if rank == 0: print("P=%d s=%d: mpk %.3f ms (n_loc=%d n_own=%d ghosts=%d)" % (world, ss, t.item(), dm.info("n_loc"), dm.n, dm.info("n_ghost")), flush=True)
+    if rank == 0: print("P=%d s=%d: mpk %.3f ms (n_loc=%d n_own=%d ghosts=%d p2p_halo=%d p2p_ar=%d)" % (world, ss, t.item(), dm.info("n_loc"), dm.n, dm.info("n_ghost"), dm.info("p2p_halo"), dm.info("p2p_allreduce")), flush=True)
+# all-reduce latency through the library: Gram of a tiny block = tsmm + all-reduce
+import ctypes as C
+X = torch.randn((8, 4096), dtype=torch.float64, device=dev); Cd = torch.zeros(64, dtype=torch.float64, device=dev); torch.cuda.synchronize()
+for p2p in (1, 0):
+    ctx.set_option("p2p", p2p) if False else None
+def g(): ctx.lib.calz_gram(ctx.h, 4096, 8, X.data_ptr(), 4096, 8, X.data_ptr(), 4096, Cd.data_ptr())
+for _ in range(20): g()
+ctx.sync(); dist.barrier()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(stream)
+for _ in range(200): g()
+e1.record(stream); e1.synchronize()
+if rank == 0: print("P=%d tiny gram + allreduce: %.1f us per call" % (world, e0.elapsed_time(e1) / 200 * 1e3), flush=True)
 dist.destroy_process_group()
