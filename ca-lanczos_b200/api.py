@@ -13,6 +13,7 @@ There is no CPU fallback: every function raises if the CUDA library or a device 
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 
 import numpy as np
@@ -65,6 +66,9 @@ class Context:
         self.h = h
         self.device = int(device)
         self.rank, self.nranks = 0, 1
+        for kv in filter(None, os.environ.get("CALZ_OPTS", "").split(",")):      # e.g. CALZ_OPTS=mpk_persistent=0,p2p=0
+            k, v = kv.split("=")
+            self.set_option(k.strip(), int(v))
 
     def close(self):
         if getattr(self, "h", None):
