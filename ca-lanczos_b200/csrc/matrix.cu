@@ -90,11 +90,6 @@ int calz_mat_destroy(calz_mat* m) {
     if (!m) return CALZ_OK;
     if (m->ctx) cudaStreamSynchronize(m->ctx->stream);
     p2p_halo_teardown(m);
-    for (auto& kv : m->persist) {
-        if (kv.second.d_sched) cudaFree(kv.second.d_sched);
-        if (kv.second.d_done) cudaFree(kv.second.d_done);
-    }
-    if (m->d_persist_err) cudaFree(m->d_persist_err);
     void* ptrs[] = {m->d_send_idx, m->d_send_buf, m->d_rowptr, m->d_colind, m->d_val, m->d_slice_ptr,
                     m->d_sell_col, m->d_sell_val, m->d_perm, m->d_W};
     for (void* p : ptrs)

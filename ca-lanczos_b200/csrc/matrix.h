@@ -2,15 +2,6 @@
 #pragma once
 #include "calz_internal.h"
 
-#include <map>
-
-struct PersistSched {                     // wave-front schedule of the persistent MPK kernel for one value of s
-    unsigned int* d_sched = nullptr;
-    unsigned int* d_done = nullptr;
-    int nsched = 0;
-    int tlo[33] = {}, thi[33] = {};
-};
-
 struct calz_mat {
     calz_ctx* ctx = nullptr;
     int64_t n_glob = 0, row_lo = 0, row_hi = 0;      // owned global rows [row_lo,row_hi)
@@ -49,9 +40,6 @@ struct calz_mat {
     int32_t* d_sell_col = nullptr;
     double* d_sell_val = nullptr;
     int32_t* d_perm = nullptr;                       // sorted position -> local row (NULL: identity)
-
-    std::map<int, PersistSched> persist;
-    int* d_persist_err = nullptr;
 
     // basis workspace n_loc x (s_max+1), ghosts included
     double* d_W = nullptr;

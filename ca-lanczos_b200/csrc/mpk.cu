@@ -79,170 +79,6 @@ k_spmv_csr(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
     }
 }
 
-// ---- persistent MPK: all s steps in ONE launch, ordered by data-flow flags so that the slice of A in use stays in L2
-//
-// The s SpMV steps of a block read A s times; at C3 that is 11.2 of the 13.4 GB a plain MPK moves.  A[rows r..r+s*b]
-// (b = bandwidth) fits the 126 MB L2 when the steps are skewed: tile t of step k runs as soon as tiles t-G..t+G of step
-// k-1 are done (G = ceil(b/tile)), in the wave-front order  key = t + (k-1)*lag, lag = G + grid/s + 2 (all s steps are
-// in flight at once, each on its own range of tiles, step k trailing step k-1 by `lag` tiles).  CTAs are persistent and take the
-// schedule entries round-robin (entry e -> CTA e mod grid): every dependency of an entry sits at a smaller entry, every
-// CTA walks its entries in increasing order, so the smallest unfinished entry can always run -- no dead-lock, no global
-// barrier, no atomics on the critical path.  Completion flags: one word per (step, tile), release/acquire at GPU scope.
-constexpr int kPersistThreads = 512;
-constexpr int kPersistTileSlices = 32;               // 1024 rows per tile
-constexpr unsigned long long kPersistSpinLimit = 50ull * 1000ull * 1000ull;
-
-struct PersistArgs {
-    const int32_t* slice_ptr; const int32_t* col; const double* val;
-    double* W; long long ldW; long long n_loc; long long nslices;
-    int s, G, ntiles, nsched;
-    const unsigned int* sched;                        // (k << 27) | tile, wave-front order
-    unsigned int* done;                               // [s+1][ntiles]
-    int* err;
-    double shift[32], pair[32];
-    int tlo[33], thi[33];                             // active tile range of step k
-};
-
-__device__ __forceinline__ uint32_t mpk_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mpk_mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mpk_smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mpk_mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mpk_smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mpk_mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(mpk_smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-
-// four consecutive entries j..j+3 of one lane's row inside a SELL slice (predicated past the slice width)
-struct Quad { double a[4]; int32_t c[4]; };
-__device__ __forceinline__ Quad load_quad(const double* __restrict__ v, const int32_t* __restrict__ c, int j, int w, int32_t self) {
-    Quad q;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const bool ok = j + u < w;
-        q.a[u] = ok ? __ldg(v + (j + u) * 32) : 0.0;
-        q.c[u] = ok ? __ldg(c + (j + u) * 32) : self;
-    }
-    return q;
-}
-
-// two slices per warp with all loads of a round in flight together (the persistent kernel has fewer warps per SM than
-// the one-slice-per-warp kernel, so the memory-level parallelism has to come from the instruction stream)
-template <bool NEWTON>
-__device__ __forceinline__ void sell_slice_pair(const PersistArgs& a, long long s0, long long s1, int lane, const double* __restrict__ x,
-                                                const double* __restrict__ xprev, double* __restrict__ y, double shift, double pair) {
-    const bool has1 = s1 < a.nslices;
-    const int32_t p00 = __ldg(a.slice_ptr + s0), p01 = __ldg(a.slice_ptr + s0 + 1);
-    const int32_t p10 = has1 ? __ldg(a.slice_ptr + s1) : 0, p11 = has1 ? __ldg(a.slice_ptr + s1 + 1) : 0;
-    const double* __restrict__ v0 = a.val + (long long)p00 * 32 + lane;
-    const int32_t* __restrict__ c0 = a.col + (long long)p00 * 32 + lane;
-    const double* __restrict__ v1 = a.val + (long long)p10 * 32 + lane;
-    const int32_t* __restrict__ c1 = a.col + (long long)p10 * 32 + lane;
-    const int w0 = p01 - p00, w1 = p11 - p10;
-    const long long r0 = s0 * 32 + lane, r1 = s1 * 32 + lane;
-    const int32_t self0 = (int32_t)min(r0, a.n_loc - 1), self1 = (int32_t)min(has1 ? r1 : r0, a.n_loc - 1);
-    double sum0 = 0.0, sum1 = 0.0;
-    const int wmax = max(w0, w1);
-    for (int j = 0; j < wmax; j += 4) {
-        const Quad q0 = load_quad(v0, c0, j, w0, self0);
-        const Quad q1 = load_quad(v1, c1, j, w1, self1);
-        double x0[4], x1[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { x0[u] = x[q0.c[u]]; x1[u] = x[q1.c[u]]; }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) { sum0 = fma(q0.a[u], x0[u], sum0); sum1 = fma(q1.a[u], x1[u], sum1); }
-    }
-    if (r0 < a.n_loc) {
-        if (NEWTON) sum0 = newton_epilogue(sum0, x[r0], pair != 0.0 ? xprev[r0] : 0.0, shift, pair);
-        y[r0] = sum0;
-    }
-    if (has1 && r1 < a.n_loc) {
-        if (NEWTON) sum1 = newton_epilogue(sum1, x[r1], pair != 0.0 ? xprev[r1] : 0.0, shift, pair);
-        y[r1] = sum1;
-    }
-}
-
-// warp 0 = control (dependency polling, completion flags), warps 1..16 = compute; two tiles in flight per CTA
-template <bool NEWTON>
-__global__ void __launch_bounds__(kPersistThreads + 32, 2)
-k_mpk_persistent(PersistArgs a) {
-    __shared__ uint64_t ready[2], finished[2];
-    __shared__ int bail;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int CW = kPersistThreads / 32;             // compute warps
-    if (threadIdx.x == 0) {
-        bail = 0;
-        mpk_mbar_init(&ready[0], 1); mpk_mbar_init(&ready[1], 1);
-        mpk_mbar_init(&finished[0], CW); mpk_mbar_init(&finished[1], CW);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (warp == 0) {
-        // ======================================================= control warp
-        int i = 0, prev_k = 0, prev_t = 0;
-        for (int e = blockIdx.x; e < a.nsched; e += gridDim.x, ++i) {
-            const unsigned int ent = a.sched[e];
-            const int k = (int)(ent >> 27), t = (int)(ent & ((1u << 27) - 1));
-            if (k > 1) {
-                // wait for tiles [t-G, t+G] of step k-1 (clipped to that step's active range)
-                const int lo = max(t - a.G, a.tlo[k - 1]), hi = min(t + a.G + 1, a.thi[k - 1]);
-                const volatile unsigned int* d = a.done + (size_t)(k - 1) * a.ntiles;
-                unsigned long long it = 0;
-                while (true) {
-                    bool ok = true;
-                    for (int j = lo + lane; j < hi; j += 32) ok &= (d[j] != 0u);
-                    if (__all_sync(0xffffffffu, ok)) break;
-                    if (++it > kPersistSpinLimit || (it % 1024 == 0 && *(volatile int*)a.err)) {
-                        if (lane == 0) { *(volatile int*)a.err = 2; bail = 1; }
-                        break;
-                    }
-                }
-                __threadfence();                       // acquire (also drops stale L1 lines of this SM)
-            }
-            __syncwarp();
-            if (lane == 0) mpk_mbar_arrive(&ready[i & 1]);
-            if (i > 0) {                               // publish the previous tile while the compute warps work on this one
-                mpk_mbar_wait(&finished[(i - 1) & 1], (uint32_t)(((i - 1) >> 1) & 1));
-                if (lane == 0) {
-                    __threadfence();                   // release: the tile's rows before its flag
-                    *((volatile unsigned int*)a.done + (size_t)prev_k * a.ntiles + prev_t) = 1u;
-                }
-            }
-            prev_k = k; prev_t = t;
-            if (bail) break;
-        }
-        if (i > 0 && !bail) {
-            mpk_mbar_wait(&finished[(i - 1) & 1], (uint32_t)(((i - 1) >> 1) & 1));
-            if (lane == 0) {
-                __threadfence();
-                *((volatile unsigned int*)a.done + (size_t)prev_k * a.ntiles + prev_t) = 1u;
-            }
-        }
-    } else {
-        // ======================================================= compute warps
-        const int cw = warp - 1;
-        int i = 0;
-        for (int e = blockIdx.x; e < a.nsched; e += gridDim.x, ++i) {
-            const unsigned int ent = a.sched[e];
-            const int k = (int)(ent >> 27), t = (int)(ent & ((1u << 27) - 1));
-            mpk_mbar_wait(&ready[i & 1], (uint32_t)((i >> 1) & 1));
-            if (*(volatile int*)&bail) return;
-            const double* x = a.W + (long long)(k - 1) * a.ldW;
-            const double* xp = (k >= 2) ? a.W + (long long)(k - 2) * a.ldW : x;
-            double* y = a.W + (long long)k * a.ldW;
-            const long long s0 = (long long)t * kPersistTileSlices + cw;
-            if (s0 < a.nslices) sell_slice_pair<NEWTON>(a, s0, s0 + CW, lane, x, xp, y, a.shift[k - 1], a.pair[k - 1]);
-            __syncwarp();
-            if (lane == 0) mpk_mbar_arrive(&finished[i & 1]);
-        }
-    }
-}
-
 __global__ void k_pack(const double* __restrict__ x, const int32_t* __restrict__ idx, double* __restrict__ buf, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) buf[i] = x[idx[i]];
@@ -371,58 +207,6 @@ int mpk_run(calz_mat* m, const double* v, int s, const Shifts& sh) {
     if (ctx->opt_l2_chunk_bytes > 0 && bytes_per_row > 0) {
         chunk_rows = round_up(std::max<int64_t>(ctx->opt_l2_chunk_bytes / bytes_per_row, gran), gran);
         if (chunk_rows < 2 * bwid || chunk_rows >= m->n_loc) chunk_rows = 0;   // band too wide / matrix fits: plain sweeps
-    }
-    // ---- persistent data-flow kernel (SELL without row permutation, wave-front window fits in L2)
-    if (ctx->opt_mpk_persistent && m->layout == CALZ_LAYOUT_SELL && !m->d_perm && s <= 31) {
-        const long long TR = 32LL * kPersistTileSlices;
-        const int ntiles = (int)((m->n_loc + TR - 1) / TR);
-        const int G = (int)((m->bandwidth + TR - 1) / TR);
-        int per_sm = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_mpk_persistent<true>, kPersistThreads + 32, 0);
-        const int grid = std::min(ctx->num_sms * std::max(1, std::min(per_sm, 2)), std::max(1, ntiles));
-        // lag between consecutive steps: the dependency reach G plus the tiles of one step that are in flight at the same
-        // time (grid/s), so that everything an entry waits for sits at least `grid` schedule positions behind it
-        const int lag = G + (grid + s - 1) / s + 2;
-        const long long window_tiles = (long long)(s - 1) * lag + grid;
-        const long long window_bytes = window_tiles * TR * bytes_per_row;
-        if (per_sm >= 1 && ntiles >= 4 * grid && G + 1 < ntiles && window_bytes <= ctx->opt_mpk_l2_window_bytes) {
-            PersistSched& ps = m->persist[s];
-            if (!ps.d_sched) {
-                std::vector<std::pair<long long, unsigned int>> ent;
-                for (int k = 1; k <= s; ++k) {
-                    ps.tlo[k] = (int)(lo_of(k) / TR);
-                    ps.thi[k] = (int)std::min<long long>(ntiles, (hi_of(k) + TR - 1) / TR);
-                    for (int t = ps.tlo[k]; t < ps.thi[k]; ++t)
-                        ent.push_back({(long long)t + (long long)(k - 1) * lag, ((unsigned int)k << 27) | (unsigned int)t});
-                }
-                ps.tlo[0] = 0; ps.thi[0] = ntiles;
-                std::stable_sort(ent.begin(), ent.end(), [](const std::pair<long long, unsigned int>& x, const std::pair<long long, unsigned int>& y) {
-                    return x.first < y.first; });
-                std::vector<unsigned int> sched(ent.size());
-                for (size_t i = 0; i < ent.size(); ++i) sched[i] = ent[i].second;
-                ps.nsched = (int)sched.size();
-                CALZ_CUDA(ctx, cudaMalloc(&ps.d_sched, std::max<size_t>(sched.size(), 1) * sizeof(unsigned int)));
-                CALZ_CUDA(ctx, cudaMemcpyAsync(ps.d_sched, sched.data(), sched.size() * sizeof(unsigned int), cudaMemcpyHostToDevice, ctx->stream));
-                CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                CALZ_CUDA(ctx, cudaMalloc(&ps.d_done, (size_t)(s + 1) * ntiles * sizeof(unsigned int)));
-                if (!m->d_persist_err) {
-                    CALZ_CUDA(ctx, cudaMalloc(&m->d_persist_err, 64));
-                    CALZ_CUDA(ctx, cudaMemset(m->d_persist_err, 0, 64));
-                }
-            }
-            CALZ_CUDA(ctx, cudaMemsetAsync(ps.d_done, 0, (size_t)(s + 1) * ntiles * sizeof(unsigned int), ctx->stream));
-            PersistArgs a{};
-            a.slice_ptr = m->d_slice_ptr; a.col = m->d_sell_col; a.val = m->d_sell_val;
-            a.W = W; a.ldW = ld; a.n_loc = m->n_loc; a.nslices = m->sell_slices;
-            a.s = s; a.G = G; a.ntiles = ntiles; a.nsched = ps.nsched; a.sched = ps.d_sched; a.done = ps.d_done; a.err = m->d_persist_err;
-            for (int k = 0; k < s; ++k) { a.shift[k] = sh.re[k]; a.pair[k] = sh.pair[k]; }
-            for (int k = 0; k <= s; ++k) { a.tlo[k] = ps.tlo[k]; a.thi[k] = ps.thi[k]; }
-            if (sh.newton) k_mpk_persistent<true><<<grid, kPersistThreads + 32, 0, ctx->stream>>>(a);
-            else k_mpk_persistent<false><<<grid, kPersistThreads + 32, 0, ctx->stream>>>(a);
-            CALZ_LAUNCH_CHECK(ctx);
-            if (m->p2p_halo) CALZ_TRY(p2p_halo_ack(m));
-            return CALZ_OK;
-        }
     }
     if (chunk_rows == 0) {
         for (int k = 1; k <= s; ++k) CALZ_TRY(step(k, 0, m->n_loc));
