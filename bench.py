@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--mz", type=int, default=0, help="z extent (default m): --mz 32 is the per-rank share of the 8-GPU run")
     ap.add_argument("--s", type=int, default=8)
     ap.add_argument("--backend", default="cholqr2", choices=["cholqr", "cholqr2", "tsqr"])
-    ap.add_argument("--layout", default="sell", choices=["sell", "csr", "auto"])
+    ap.add_argument("--layout", default="auto", choices=["auto", "selld", "sell", "csr"])
     ap.add_argument("--l2-chunk-mb", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libcalz.so")
 
 OK = 0
 ERR_CHOL = 4
-LAYOUT = {"auto": 0, "csr": 1, "sell": 2}
+LAYOUT = {"auto": 0, "csr": 1, "sell": 2, "selld": 3}
 LAYOUT_NAME = {v: k for k, v in LAYOUT.items()}
 QR = {"tsqr": 0, "cholqr": 1, "cholqr2": 2}
 

@@ -81,6 +81,7 @@ struct calz_ctx {
     int64_t opt_sell_sigma = 0;      // 0: choose
     int64_t opt_csr_lanes = 0;       // 0: choose
     int64_t opt_cholqr2_inv_thresh = 32;
+    int64_t opt_sell_dict = 1;       // layout=auto may pick the dictionary-coded SELL variant
     int64_t opt_p2p = 1;             // peer-memory all-reduce / halo push instead of NCCL (when IPC works)
     calz::P2P p2p;
     int64_t opt_tile_pipeline = 1;   // fused TMA-tile passes in projectAndNormalize (0: legacy kernels)

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
 #include <numeric>
 
 #include "matrix.h"
@@ -90,7 +91,7 @@ int calz_mat_destroy(calz_mat* m) {
     if (!m) return CALZ_OK;
     if (m->ctx) cudaStreamSynchronize(m->ctx->stream);
     p2p_halo_teardown(m);
-    void* ptrs[] = {m->d_send_idx, m->d_send_buf, m->d_rowptr, m->d_colind, m->d_val, m->d_slice_ptr,
+    void* ptrs[] = {m->d_codes, m->d_dict, m->d_send_idx, m->d_send_buf, m->d_rowptr, m->d_colind, m->d_val, m->d_slice_ptr,
                     m->d_sell_col, m->d_sell_val, m->d_perm, m->d_W};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -337,6 +338,38 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
             perm.swap(p2);
         }
     }
+    // ---- dictionary-coded SELL: one byte per non-zero when the matrix has <= 255 distinct (column offset, value) pairs
+    //      (every constant-coefficient stencil; lossless, same arithmetic order as CSR/SELL)
+    std::vector<int32_t> dict_off;
+    std::vector<double> dict_val;
+    std::vector<uint8_t> codes;          // per CSR entry
+    bool dict_ok = (layout == CALZ_LAYOUT_AUTO || layout == CALZ_LAYOUT_SELL_DICT) && m->nnz_loc > 0;
+    if (dict_ok) {
+        std::map<std::pair<int32_t, uint64_t>, int> lut;
+        codes.resize((size_t)m->nnz_loc);
+        for (int64_t l = 0; l < n_loc && dict_ok; ++l)
+            for (int32_t e = h_rowptr[l]; e < h_rowptr[l + 1]; ++e) {
+                uint64_t bits;
+                memcpy(&bits, &h_val[e], 8);
+                auto key = std::make_pair((int32_t)(h_col[e] - (int32_t)l), bits);
+                auto it = lut.find(key);
+                if (it == lut.end()) {
+                    if (lut.size() >= 255) { dict_ok = false; break; }
+                    it = lut.emplace(key, (int)lut.size()).first;
+                    dict_off.push_back(key.first);
+                    dict_val.push_back(h_val[e]);
+                }
+                codes[e] = (uint8_t)it->second;
+            }
+        int32_t wmax = 0;
+        for (int64_t l = 0; l < n_loc; ++l) wmax = std::max(wmax, rowlen[l]);
+        if (wmax > 64) dict_ok = false;                       // very long rows: the byte stream per lane gets too ragged
+    }
+    if (layout == CALZ_LAYOUT_SELL_DICT && !dict_ok) {
+        delete m;
+        return set_error(ctx, CALZ_ERR_UNSUPPORTED, "SELL_DICT layout needs <= 255 distinct (offset, value) pairs and rows <= 64 entries");
+    }
+    if (layout == CALZ_LAYOUT_AUTO && dict_ok && ctx->opt_sell_dict) layout = CALZ_LAYOUT_SELL_DICT;
     if (layout == CALZ_LAYOUT_AUTO)
         layout = (m->nnz_loc > 0 && (double)padded <= 1.30 * (double)m->nnz_loc && padded < (int64_t)2147483647)
                      ? CALZ_LAYOUT_SELL : CALZ_LAYOUT_CSR;
@@ -344,7 +377,34 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
         layout = CALZ_LAYOUT_CSR;
     m->layout = layout;
 
-    if (layout == CALZ_LAYOUT_CSR) {
+    if (layout == CALZ_LAYOUT_SELL_DICT) {
+        // per slice of 32 rows: ceil(width/8) blocks of 32 lanes x 8 code bytes (one coalesced 256-B load per block)
+        std::vector<int32_t> slice_ptr(m->sell_slices + 1, 0);
+        int64_t blocks = 0;
+        for (int64_t sl = 0; sl < m->sell_slices; ++sl) {
+            int32_t w = 0;
+            for (int64_t r = sl * C; r < std::min<int64_t>(n_loc, sl * C + C); ++r) w = std::max(w, rowlen[r]);
+            slice_ptr[sl] = (int32_t)blocks;
+            blocks += (w + 7) / 8;
+        }
+        slice_ptr[m->sell_slices] = (int32_t)blocks;
+        std::vector<uint8_t> packed((size_t)blocks * 256, (uint8_t)255);        // 255 = padding code
+        for (int64_t sl = 0; sl < m->sell_slices; ++sl)
+            for (int64_t r = sl * C; r < std::min<int64_t>(n_loc, sl * C + C); ++r)
+                for (int32_t j = 0; j < rowlen[r]; ++j)
+                    packed[((size_t)(slice_ptr[sl] + j / 8) * 32 + (size_t)(r - sl * C)) * 8 + (j % 8)] = codes[h_rowptr[r] + j];
+        std::vector<double> dict(2 * 256, 0.0);                                   // {value, offset-as-int64 bits} pairs, 16 B each
+        for (size_t k = 0; k < dict_val.size(); ++k) {
+            dict[2 * k] = dict_val[k];
+            long long o = dict_off[k];
+            memcpy(&dict[2 * k + 1], &o, 8);
+        }
+        m->sell_padded = blocks * 256;
+        m->dict_size = (int)dict_val.size();
+        CALZ_TRY(upload(ctx, &m->d_slice_ptr, slice_ptr));
+        CALZ_TRY(upload(ctx, &m->d_codes, packed));
+        CALZ_TRY(upload(ctx, &m->d_dict, dict));
+    } else if (layout == CALZ_LAYOUT_CSR) {
         CALZ_TRY(upload(ctx, &m->d_rowptr, h_rowptr));
         CALZ_TRY(upload(ctx, &m->d_colind, h_col));
         CALZ_TRY(upload(ctx, &m->d_val, h_val));
@@ -443,6 +503,7 @@ int calz_mat_info(const calz_mat* m, const char* what, int64_t* value) {
     else if (!strcmp(what, "bandwidth")) *value = m->bandwidth;
     else if (!strcmp(what, "s_max")) *value = m->s_max;
     else if (!strcmp(what, "ldW")) *value = m->ldW;
+    else if (!strcmp(what, "dict_size")) *value = m->dict_size;
     else if (!strcmp(what, "p2p_halo")) *value = m->p2p_halo ? 1 : 0;
     else if (!strcmp(what, "p2p_allreduce")) *value = (m->ctx && m->ctx->p2p.enabled) ? 1 : 0;
     else return set_error(m->ctx, CALZ_ERR_BADARG, "calz_mat_info: unknown key '%s'", what);

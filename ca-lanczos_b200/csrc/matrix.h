@@ -41,6 +41,11 @@ struct calz_mat {
     double* d_sell_val = nullptr;
     int32_t* d_perm = nullptr;                       // sorted position -> local row (NULL: identity)
 
+    // dictionary-coded SELL: 8 code bytes per lane per block, dictionary of {value, offset} pairs
+    uint8_t* d_codes = nullptr;
+    double* d_dict = nullptr;
+    int dict_size = 0;
+
     // basis workspace n_loc x (s_max+1), ghosts included
     double* d_W = nullptr;
     int64_t ldW = 0;

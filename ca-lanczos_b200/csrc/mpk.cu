@@ -57,6 +57,69 @@ k_spmv_sell(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ c
     }
 }
 
+// ---- dictionary-coded SELL: one warp per slice, one lane per row; each lane pulls 8 code bytes per 64-bit load and looks
+//      {value, column offset} up in a 4 KB dictionary that lives in L1.  Same summation order as CSR/SELL (bit-identical).
+constexpr int kDictSlicesPerWarp = 2;     // independent slices per warp: the loads of both are in flight together
+
+template <bool NEWTON>
+__global__ void __launch_bounds__(kSpmvThreads)
+k_spmv_selld(const int32_t* __restrict__ slice_ptr, const uint2* __restrict__ codes, const double2* __restrict__ dict, int dict_size,
+             const double* __restrict__ x, const double* __restrict__ xprev, double* __restrict__ y, int64_t slice_lo,
+             int64_t slice_hi, int64_t n_loc, double shift, double pair) {
+    constexpr int NS = kDictSlicesPerWarp;
+    // dictionary in shared memory, split into values and 32-bit offsets (broadcast / conflict-light reads)
+    __shared__ double sval[256];
+    __shared__ int soff[256];
+    for (int i = threadIdx.x; i < 256; i += kSpmvThreads) {
+        const double2 e = i < dict_size ? __ldg(dict + i) : make_double2(0.0, 0.0);
+        sval[i] = e.x;
+        soff[i] = (int)__double_as_longlong(e.y);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t slice0 = slice_lo + ((int64_t)blockIdx.x * (kSpmvThreads / 32) + (threadIdx.x >> 5)) * NS;
+    if (slice0 >= slice_hi) return;
+    int32_t p0[NS], nb[NS];
+    int maxb = 0;
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        const bool ok = slice0 + i < slice_hi;
+        p0[i] = ok ? __ldg(slice_ptr + slice0 + i) : 0;
+        nb[i] = ok ? __ldg(slice_ptr + slice0 + i + 1) - p0[i] : 0;
+        maxb = max(maxb, nb[i]);
+    }
+    double sum[NS];
+    int row[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        sum[i] = 0.0;
+        row[i] = (int)min((slice0 + i) * 32 + lane, n_loc - 1);
+    }
+    for (int b = 0; b < maxb; ++b) {
+        uint2 w[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) w[i] = (b < nb[i]) ? __ldg(codes + (int64_t)(p0[i] + b) * 32 + lane) : make_uint2(~0u, ~0u);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                const unsigned int half = q < 4 ? w[i].x : w[i].y;
+                const unsigned int c = (half >> (8 * (q & 3))) & 0xffu;
+                if (c != 255u) sum[i] = fma(sval[c], x[row[i] + soff[c]], sum[i]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        const int64_t r = (slice0 + i) * 32 + lane;
+        if (slice0 + i < slice_hi && r < n_loc) {
+            double v = sum[i];
+            if (NEWTON) v = newton_epilogue(v, x[r], pair != 0.0 ? xprev[r] : 0.0, shift, pair);
+            y[r] = v;
+        }
+    }
+}
+
 // ---- CSR: L lanes per row (L chosen from the mean row length), shuffle reduction
 template <int L, bool NEWTON>
 __global__ void __launch_bounds__(kSpmvThreads)
@@ -109,6 +172,19 @@ int spmv_step(calz_mat* m, const double* x, const double* xp, double* y, int64_t
               double shift, double pair) {
     if (hi <= lo) return CALZ_OK;
     calz_ctx* ctx = m->ctx;
+    if (m->layout == CALZ_LAYOUT_SELL_DICT) {
+        const int64_t s0 = lo / 32, s1 = (hi + 31) / 32;
+        const int64_t per_cta = (int64_t)(kSpmvThreads / 32) * kDictSlicesPerWarp;
+        const unsigned grid = (unsigned)((s1 - s0 + per_cta - 1) / per_cta);
+        const uint2* codes = (const uint2*)m->d_codes;
+        const double2* dict = (const double2*)m->d_dict;
+        if (newton)
+            k_spmv_selld<true><<<grid, kSpmvThreads, 0, ctx->stream>>>(m->d_slice_ptr, codes, dict, m->dict_size, x, xp, y, s0, s1, m->n_loc, shift, pair);
+        else
+            k_spmv_selld<false><<<grid, kSpmvThreads, 0, ctx->stream>>>(m->d_slice_ptr, codes, dict, m->dict_size, x, xp, y, s0, s1, m->n_loc, 0.0, 0.0);
+        CALZ_LAUNCH_CHECK(ctx);
+        return CALZ_OK;
+    }
     if (m->layout == CALZ_LAYOUT_SELL) {
         const int64_t s0 = lo / 32, s1 = (hi + 31) / 32;
         const unsigned grid = (unsigned)((s1 - s0 + kSpmvThreads / 32 - 1) / (kSpmvThreads / 32));
@@ -188,7 +264,7 @@ int mpk_run(calz_mat* m, const double* v, int s, const Shifts& sh) {
         CALZ_CUDA(ctx, cudaMemcpyAsync(W + m->own_off, v, (size_t)m->n_own * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     CALZ_TRY(halo_exchange(m, W));
 
-    const int64_t gran = (m->layout == CALZ_LAYOUT_SELL) ? (m->d_perm ? m->sell_sigma : 32) : 1;
+    const int64_t gran = (m->layout == CALZ_LAYOUT_SELL) ? (m->d_perm ? m->sell_sigma : 32) : (m->layout == CALZ_LAYOUT_SELL_DICT ? 32 : 1);
     auto lo_of = [&](int k) { return (m->hull_lo[s - k] / gran) * gran; };
     auto hi_of = [&](int k) { return std::min<int64_t>(m->n_loc, round_up(m->hull_hi[s - k], gran)); };
     auto step = [&](int k, int64_t lo, int64_t hi) -> int {

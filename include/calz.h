@@ -41,6 +41,8 @@ extern "C" {
 #define CALZ_LAYOUT_AUTO        0
 #define CALZ_LAYOUT_CSR         1
 #define CALZ_LAYOUT_SELL        2
+#define CALZ_LAYOUT_SELL_DICT   3   /* SELL-32 with one dictionary code byte per non-zero: needs <= 255 distinct
+                                       (column offset, value) pairs (constant-coefficient stencils); lossless */
 
 /* QR backend at the normalize.m:14 seam */
 #define CALZ_QR_TSQR            0   /* tsqr.m:7-12   (reference default) */

@@ -74,6 +74,37 @@ def test_newton_basis(name, layout):
     assert relcols(V0, Vo) < TOL
 
 
+@pytest.mark.parametrize("name", ["poisson100", "lap3d", "tiny"])
+def test_dictionary_coded_sell_is_bit_identical(name):
+    # constant-coefficient stencils have a handful of distinct (offset, value) pairs: one code byte per non-zero,
+    # same summation order => not a single bit may differ from the plain SELL kernel; layout=auto picks it by itself
+    A = MATS[name]()
+    n = A.shape[0]
+    v = np.sin(0.37 * np.arange(n)) + 1.2
+    lam = np.array([7.9, 0.1, 4.0, 6.0, 2.0])
+    outs = {}
+    for layout in ("sell", "selld", "auto"):
+        dm = api.DeviceMatrix(A, 6, layout)
+        if layout != "sell":
+            assert dm.layout == "selld" and 0 < dm.info("dict_size") <= 9
+        outs[layout] = (api.matrix_powers_newton(dm, v, 5, lam, 1), api.matrix_powers_monomial(dm, v, 4), api.SpMV(dm, v))
+        dm.close()
+    for k in ("selld", "auto"):
+        for a, b in zip(outs["sell"], outs[k]):
+            np.testing.assert_array_equal(a, b)
+    assert relcols(outs["selld"][0], kernels.matrix_powers_newton(A, v, 5, lam, 1)) < TOL
+
+
+def test_dictionary_coded_sell_falls_back_when_values_are_not_few():
+    A = MATS["diag20000"]()                     # 20000 distinct values
+    with pytest.raises(api.CalzError):
+        api.DeviceMatrix(A, 4, "selld")
+    dm = api.DeviceMatrix(A, 4, "auto")
+    assert dm.layout == "sell"
+    A = MATS["random"]()
+    assert api.DeviceMatrix(A, 4, "auto").layout in ("sell", "csr")
+
+
 def test_newton_complex_pair_and_errors():
     A = gallery.poisson2d(30)
     v = np.sin(np.arange(900.0)) + 2

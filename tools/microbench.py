@@ -21,7 +21,7 @@ def main():
     ap.add_argument("--m", type=int, default=256)
     ap.add_argument("--s", type=int, default=8)
     ap.add_argument("--reps", type=int, default=10)
-    ap.add_argument("--layouts", default="sell,csr")
+    ap.add_argument("--layouts", default="selld,sell,csr")
     ap.add_argument("--chunks", default="0")
     ap.add_argument("--skip-orth", action="store_true")
     ap.add_argument("--skip-mpk", action="store_true")
