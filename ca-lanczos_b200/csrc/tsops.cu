@@ -389,6 +389,26 @@ __global__ void k_norm_drop(int c, const double* __restrict__ R, const double* _
     norm_drop_flag(c, A, nb2, nb2_stride, flag_out, lane);
 }
 
+// the same test from the Gram matrix of Y: ||R(:,i)|| = ||Y(:,i)|| = sqrt(G_ii), no factorisation of Y needed
+__global__ void k_norm_drop_gram(int c, const double* __restrict__ G, int ldG, const double* __restrict__ nb2, int nb2_stride, int* flag_out) {
+    const int lane = threadIdx.x;
+    double worst = 0.0;
+    if (lane < c) {
+        const double na = sqrt(G[(size_t)lane * ldG + lane]), nb = sqrt(nb2[(size_t)lane * nb2_stride]);
+        const double rel = fabs(nb - na) / nb;
+        worst = (rel == rel) ? rel : 0.0;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) worst = fmax(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+    if (lane == 0) *flag_out = worst > 0.5 ? 1 : 0;
+}
+
+int norm_drop_from_gram(calz_ctx* ctx, int c, const double* G_dev, int ldG, const double* nb2, int nb2_stride, int* flag_out) {
+    k_norm_drop_gram<<<1, 32, 0, ctx->stream>>>(c, G_dev, ldG, nb2, nb2_stride, flag_out);
+    CALZ_LAUNCH_CHECK(ctx);
+    return CALZ_OK;
+}
+
 int norm_drop_decision(calz_ctx* ctx, int c, const double* R_dev, const double* nb2, int nb2_stride, int* flag_out) {
     k_norm_drop<<<1, 32, 0, ctx->stream>>>(c, R_dev, nb2, nb2_stride, flag_out);
     CALZ_LAUNCH_CHECK(ctx);

@@ -55,6 +55,7 @@ bool tile_path_ok(int64_t n, const double* Q, int64_t ldQ, int M, const double* 
 int tile_pass(calz_ctx* ctx, int mode, int64_t n, const double* Q, int64_t ldQ, int M, const double* X, int64_t ldX, int c,
               const double* C_dev, int ldC, double* Y, int64_t ldY, double* S_dev, int ldS, const int* pred, int want, bool allreduce);
 
+int norm_drop_from_gram(calz_ctx* ctx, int c, const double* G_dev, int ldG, const double* nb2, int nb2_stride, int* flag_out);
 // same decision for a backend that already has R on the device (TSQR)
 int norm_drop_decision(calz_ctx* ctx, int c, const double* R_dev, const double* nb2, int nb2_stride, int* flag_out);
 

@@ -231,17 +231,17 @@ int run_apply(calz_ctx* ctx, const Level& L, int c, const double* W, long long l
     return CALZ_OK;
 }
 
-int rpl_for(int c) { return c <= 16 ? 4 : 2; }
+int rpl_for(int c) { return c <= 8 ? 8 : (c <= 16 ? 4 : 2); }
 
 int dispatch_leaf(calz_ctx* ctx, const Level& L, int c, const double* A, long long ldA, const int* pred, int want) {
-    if (c <= 8) return run_leaf<8, 4>(ctx, L, c, A, ldA, pred, want);
+    if (c <= 8) return run_leaf<8, 8>(ctx, L, c, A, ldA, pred, want);
     if (c <= 16) return run_leaf<16, 4>(ctx, L, c, A, ldA, pred, want);
     if (c <= 24) return run_leaf<24, 2>(ctx, L, c, A, ldA, pred, want);
     return run_leaf<32, 2>(ctx, L, c, A, ldA, pred, want);
 }
 
 int dispatch_apply(calz_ctx* ctx, const Level& L, int c, const double* W, long long ldW, double* Out, long long ldOut) {
-    if (c <= 8) return run_apply<8, 4>(ctx, L, c, W, ldW, Out, ldOut);
+    if (c <= 8) return run_apply<8, 8>(ctx, L, c, W, ldW, Out, ldOut);
     if (c <= 16) return run_apply<16, 4>(ctx, L, c, W, ldW, Out, ldOut);
     if (c <= 24) return run_apply<24, 2>(ctx, L, c, W, ldW, Out, ldOut);
     return run_apply<32, 2>(ctx, L, c, W, ldW, Out, ldOut);
