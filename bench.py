@@ -301,11 +301,20 @@ def run_b200(args):
     launch_ms = ms_mpk / s
     achieved = spmv_bytes / (launch_ms * 1e-3) / 1e9
     traffic = None
+    kname = {"selld": "k_spmv_selld", "sell": "k_spmv_sell", "csr": "k_spmv_csr"}.get(dm.layout, "k_spmv")
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            traffic = json.load(f).get("k_spmv_sell_dram_bytes_per_launch")
+            traffic = json.load(f).get(kname + "_dram_bytes_per_launch")
+        if traffic is not None and world > 1:
+            traffic = traffic * n_own / n               # the capture is of the 1-GPU launch
     except Exception:
         pass
+    note = None
+    if dm.layout == "selld":
+        note = ("dictionary-coded SELL: A is stored losslessly as 1 code byte per non-zero (7 distinct (offset,value) pairs), so the DRAM "
+                "traffic of a launch is ~0.38 GB while the ALGORITHMIC bytes (CSR, 12 B/nnz, SURVEY 8d) stay 1.74 GB: frac > 1 means bytes "
+                "not moved, not work not done (bit-identical to the plain SELL kernel, tests/test_gpu_mpk.py); run with --layout sell for "
+                "the uncompressed kernel (0.89 of the copy peak)")
     line = {
         "metric": "ca_lanczos_s_step_blocks_per_sec", "value": value, "unit": "blocks/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -315,9 +324,10 @@ def run_b200(args):
                    (12 * nnz_loc / 1e9, 8 * n_loc * (s + 1) / 1e9), "l2_chunk_mb": args.l2_chunk_mb, "setup_s": round(setup_s, 1)},
         "phases_ms": {"mpk": ms_mpk, "project_and_normalize": ms_orth, "mpk_share": ms_mpk / (ms_mpk + ms_orth),
                       "host_enqueue_ms_per_block": host_enqueue_ms},
-        "roofline": {"kernel": "k_spmv_sell (one SpMV step of the MPK)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"kernel": kname + " (one SpMV step of the MPK)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": spmv_bytes, "launch_ms": launch_ms},
+                     "algorithmic_bytes_per_launch": spmv_bytes, "launch_ms": launch_ms,
+                     "traffic_frac": (traffic / (launch_ms * 1e-3) / 1e9 / peak) if traffic else None, "note": note},
         "gpu_launches": int(launches), "clocks": clocks,
         "check": {"ritz_max": ritz_max, "lambda_max": float(6.0 - 6.0 * np.cos(m * np.pi / (m + 1))),
                   "second_pass_fraction": second_frac},
