@@ -81,6 +81,9 @@ struct calz_ctx {
     int64_t opt_sell_sigma = 0;      // 0: choose
     int64_t opt_csr_lanes = 0;       // 0: choose
     int64_t opt_cholqr2_inv_thresh = 32;
+    int64_t opt_mpk_xs_rows = 0;     // cap on the rows per CTA of the TMA-staged kernel (0: 2048)
+    int64_t opt_mpk_tma_x = 0;       // dictionary SELL: stage the x segments of a CTA in shared memory with TMA bulk copies
+                                     // (measured at C3: 1.45 ms per MPK vs 1.19 ms for the L1-gather kernel => opt-in)
     int64_t opt_sell_dict = 1;       // layout=auto may pick the dictionary-coded SELL variant
     int64_t opt_p2p = 1;             // peer-memory all-reduce / halo push instead of NCCL (when IPC works)
     calz::P2P p2p;

@@ -234,6 +234,8 @@ int calz_set_option(calz_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "cholqr2_inv_thresh")) ctx->opt_cholqr2_inv_thresh = value > 0 ? value : 32;
     else if (!strcmp(key, "p2p")) ctx->opt_p2p = value;
     else if (!strcmp(key, "sell_dict")) ctx->opt_sell_dict = value;
+    else if (!strcmp(key, "mpk_tma_x")) ctx->opt_mpk_tma_x = value;
+    else if (!strcmp(key, "mpk_xs_rows")) ctx->opt_mpk_xs_rows = value;
     else if (!strcmp(key, "tile_pipeline")) ctx->opt_tile_pipeline = value;
     else if (!strcmp(key, "grid_mult")) ctx->opt_grid_mult = value > 0 ? value : 1;
     else return set_error(ctx, CALZ_ERR_BADARG, "calz_set_option: unknown key '%s'", key);

@@ -91,7 +91,7 @@ int calz_mat_destroy(calz_mat* m) {
     if (!m) return CALZ_OK;
     if (m->ctx) cudaStreamSynchronize(m->ctx->stream);
     p2p_halo_teardown(m);
-    void* ptrs[] = {m->d_codes, m->d_dict, m->d_send_idx, m->d_send_buf, m->d_rowptr, m->d_colind, m->d_val, m->d_slice_ptr,
+    void* ptrs[] = {m->d_xs_off, m->d_codes, m->d_dict, m->d_send_idx, m->d_send_buf, m->d_rowptr, m->d_colind, m->d_val, m->d_slice_ptr,
                     m->d_sell_col, m->d_sell_val, m->d_perm, m->d_W};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -404,6 +404,38 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
         CALZ_TRY(upload(ctx, &m->d_slice_ptr, slice_ptr));
         CALZ_TRY(upload(ctx, &m->d_codes, packed));
         CALZ_TRY(upload(ctx, &m->d_dict, dict));
+        // x staging plan: for a CTA owning rows [r0, r0+R) the entries with offset o read x[r0+o .. r0+R+o); offsets whose
+        // ranges overlap are merged into one segment (one TMA bulk copy each)
+        for (int R : {2048, 1024, 512}) {
+            if (ctx->opt_mpk_xs_rows > 0 && R > ctx->opt_mpk_xs_rows) continue;
+            std::vector<int32_t> offs(dict_off);
+            std::sort(offs.begin(), offs.end());
+            offs.erase(std::unique(offs.begin(), offs.end()), offs.end());
+            int ng = 0, total = 0, omin[8], omax[8];
+            bool ok = !offs.empty();
+            for (size_t k = 0; k < offs.size() && ok; ++k) {
+                if (ng > 0 && (int64_t)offs[k] - omax[ng - 1] < R) omax[ng - 1] = offs[k];
+                else if (ng < 8) { omin[ng] = offs[k]; omax[ng] = offs[k]; ++ng; }
+                else ok = false;
+            }
+            int base[8], len[8], amin[8];
+            for (int g = 0; g < ng && ok; ++g) {
+                amin[g] = omin[g] - (((omin[g] % 2) + 2) % 2);           // even, <= omin
+                len[g] = R + (omax[g] - amin[g]) + 2;
+                len[g] += len[g] & 1;
+                base[g] = total;
+                total += len[g];
+            }
+            if (!ok || (size_t)total * 8 > 96 * 1024 || n_loc < 4 * R) continue;
+            m->xs_rows = R; m->xs_groups = ng; m->xs_total = total;
+            std::vector<int> xoff(256, 0);
+            for (int g = 0; g < ng; ++g) { m->xs_omin[g] = amin[g]; m->xs_len[g] = len[g]; m->xs_base[g] = base[g]; }
+            for (size_t k = 0; k < dict_off.size(); ++k)
+                for (int g = 0; g < ng; ++g)
+                    if (dict_off[k] >= omin[g] && dict_off[k] <= omax[g]) xoff[k] = base[g] + (dict_off[k] - amin[g]);
+            CALZ_TRY(upload(ctx, &m->d_xs_off, xoff));
+            break;
+        }
     } else if (layout == CALZ_LAYOUT_CSR) {
         CALZ_TRY(upload(ctx, &m->d_rowptr, h_rowptr));
         CALZ_TRY(upload(ctx, &m->d_colind, h_col));
@@ -504,6 +536,8 @@ int calz_mat_info(const calz_mat* m, const char* what, int64_t* value) {
     else if (!strcmp(what, "s_max")) *value = m->s_max;
     else if (!strcmp(what, "ldW")) *value = m->ldW;
     else if (!strcmp(what, "dict_size")) *value = m->dict_size;
+    else if (!strcmp(what, "xs_rows")) *value = m->xs_rows;
+    else if (!strcmp(what, "xs_groups")) *value = m->xs_groups;
     else if (!strcmp(what, "p2p_halo")) *value = m->p2p_halo ? 1 : 0;
     else if (!strcmp(what, "p2p_allreduce")) *value = (m->ctx && m->ctx->p2p.enabled) ? 1 : 0;
     else return set_error(m->ctx, CALZ_ERR_BADARG, "calz_mat_info: unknown key '%s'", what);

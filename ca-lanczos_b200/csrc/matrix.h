@@ -45,6 +45,12 @@ struct calz_mat {
     uint8_t* d_codes = nullptr;
     double* d_dict = nullptr;
     int dict_size = 0;
+    // ... and its TMA-staged kernel: x segments of a CTA's row block (merged over overlapping offsets)
+    int xs_rows = 0;                                  // rows per CTA (0: staged kernel not applicable)
+    int xs_groups = 0;
+    int xs_omin[8] = {}, xs_len[8] = {}, xs_base[8] = {};
+    int xs_total = 0;                                 // doubles of shared memory for the segments
+    int* d_xs_off = nullptr;                          // per code: position of x[row+offset] relative to (row - r0)
 
     // basis workspace n_loc x (s_max+1), ghosts included
     double* d_W = nullptr;

@@ -120,6 +120,108 @@ k_spmv_selld(const int32_t* __restrict__ slice_ptr, const uint2* __restrict__ co
     }
 }
 
+// ---- dictionary-coded SELL with the x vector staged by TMA: a CTA owns xs_rows consecutive rows; one elected thread issues
+//      one cp.async.bulk per merged x segment (own range + stencil halos / ghost zone) into shared memory, everybody waits on
+//      the mbarrier, and the inner loop is two shared-memory reads and one FMA per non-zero -- no global gathers at all.
+struct XsPlan {
+    int rows, groups, total;
+    int omin[8], len[8], base[8];
+};
+
+__device__ __forceinline__ uint32_t mpk_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool NEWTON>
+__global__ void __launch_bounds__(kSpmvThreads)
+k_spmv_selld_tma(const int32_t* __restrict__ slice_ptr, const uint2* __restrict__ codes, const double2* __restrict__ dict, int dict_size,
+                 const int* __restrict__ xs_off, XsPlan plan, const double* __restrict__ x, const double* __restrict__ xprev,
+                 double* __restrict__ y, int64_t slice_lo, int64_t slice_hi, int64_t n_loc, int64_t ldw, double shift, double pair) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* xs = reinterpret_cast<double*>(smem_raw);
+    double* sval = xs + plan.total;
+    int* soff = reinterpret_cast<int*>(sval + 256);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(soff + 256);
+    const int slices_per_cta = plan.rows / 32;
+    const int64_t s_first = slice_lo + (int64_t)blockIdx.x * slices_per_cta;
+    const int64_t r0 = s_first * 32;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mpk_smem_u32(bar)), "r"(1) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < 256; i += kSpmvThreads) {
+        sval[i] = i < dict_size ? __ldg(dict + i).x : 0.0;
+        soff[i] = i < dict_size ? __ldg(xs_off + i) : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t bytes = 0;
+        long long lo[8], hi[8];
+        for (int g = 0; g < plan.groups; ++g) {
+            lo[g] = max((long long)(r0 + plan.omin[g]), 0LL);
+            hi[g] = min((long long)(r0 + plan.omin[g] + plan.len[g]), (long long)ldw);
+            if (hi[g] > lo[g]) bytes += (uint32_t)((hi[g] - lo[g]) * 8);
+        }
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mpk_smem_u32(bar)), "r"(bytes) : "memory");
+        for (int g = 0; g < plan.groups; ++g) {
+            if (hi[g] <= lo[g]) continue;
+            double* dst = xs + plan.base[g] + (lo[g] - (r0 + plan.omin[g]));
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(mpk_smem_u32(dst)), "l"(x + lo[g]), "r"((uint32_t)((hi[g] - lo[g]) * 8)), "r"(mpk_smem_u32(bar)) : "memory");
+        }
+    }
+    // each warp owns a run of consecutive slices, processed four at a time with all index/code loads issued up front;
+    // the first batch is fetched BEFORE waiting for the x segments so that the two latencies overlap
+    constexpr int NS = 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per_warp = slices_per_cta / (kSpmvThreads / 32);
+    bool waited = false;
+    for (int i0 = warp * per_warp; i0 < (warp + 1) * per_warp; i0 += NS) {
+        int32_t p0[NS], nb[NS];
+        int maxb = 0;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const int64_t slice = s_first + i0 + i;
+            const bool ok = i0 + i < (warp + 1) * per_warp && slice < slice_hi;
+            p0[i] = ok ? __ldg(slice_ptr + slice) : 0;
+            nb[i] = ok ? __ldg(slice_ptr + slice + 1) - p0[i] : 0;
+            maxb = max(maxb, nb[i]);
+        }
+        double sum[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) sum[i] = 0.0;
+        for (int b = 0; b < maxb; ++b) {
+            uint2 w[NS];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) w[i] = (b < nb[i]) ? __ldg(codes + (int64_t)(p0[i] + b) * 32 + lane) : make_uint2(~0u, ~0u);
+            if (!waited) {   // everybody waits for the segments (once)
+                uint32_t done;
+                do {
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(done) : "r"(mpk_smem_u32(bar)), "r"(0) : "memory");
+                } while (!done);
+                waited = true;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+#pragma unroll
+                for (int i = 0; i < NS; ++i) {
+                    const unsigned int half = q < 4 ? w[i].x : w[i].y;
+                    const unsigned int c = (half >> (8 * (q & 3))) & 0xffu;
+                    if (c != 255u) sum[i] = fma(sval[c], xs[soff[c] + (i0 + i) * 32 + lane], sum[i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const int64_t r = r0 + (int64_t)(i0 + i) * 32 + lane;
+            if (nb[i] >= 0 && i0 + i < (warp + 1) * per_warp && s_first + i0 + i < slice_hi && r < n_loc) {
+                double v = sum[i];
+                if (NEWTON) v = newton_epilogue(v, x[r], pair != 0.0 ? xprev[r] : 0.0, shift, pair);
+                y[r] = v;
+            }
+        }
+    }
+}
+
 // ---- CSR: L lanes per row (L chosen from the mean row length), shuffle reduction
 template <int L, bool NEWTON>
 __global__ void __launch_bounds__(kSpmvThreads)
@@ -172,6 +274,28 @@ int spmv_step(calz_mat* m, const double* x, const double* xp, double* y, int64_t
               double shift, double pair) {
     if (hi <= lo) return CALZ_OK;
     calz_ctx* ctx = m->ctx;
+    if (m->layout == CALZ_LAYOUT_SELL_DICT && m->xs_rows > 0 && ctx->opt_mpk_tma_x) {
+        const int64_t s0 = lo / 32, s1 = (hi + 31) / 32;
+        const int spc = m->xs_rows / 32;
+        const unsigned grid = (unsigned)((s1 - s0 + spc - 1) / spc);
+        XsPlan plan{};
+        plan.rows = m->xs_rows; plan.groups = m->xs_groups; plan.total = m->xs_total;
+        for (int g = 0; g < m->xs_groups; ++g) { plan.omin[g] = m->xs_omin[g]; plan.len[g] = m->xs_len[g]; plan.base[g] = m->xs_base[g]; }
+        const size_t smem = (size_t)m->xs_total * 8 + 256 * 8 + 256 * 4 + 64;
+        const uint2* codes = (const uint2*)m->d_codes;
+        const double2* dict = (const double2*)m->d_dict;
+        if (newton) {
+            CALZ_CUDA(ctx, cudaFuncSetAttribute(k_spmv_selld_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_spmv_selld_tma<true><<<grid, kSpmvThreads, smem, ctx->stream>>>(m->d_slice_ptr, codes, dict, m->dict_size, m->d_xs_off, plan,
+                                                                              x, xp, y, s0, s1, m->n_loc, m->ldW, shift, pair);
+        } else {
+            CALZ_CUDA(ctx, cudaFuncSetAttribute(k_spmv_selld_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k_spmv_selld_tma<false><<<grid, kSpmvThreads, smem, ctx->stream>>>(m->d_slice_ptr, codes, dict, m->dict_size, m->d_xs_off, plan,
+                                                                               x, xp, y, s0, s1, m->n_loc, m->ldW, 0.0, 0.0);
+        }
+        CALZ_LAUNCH_CHECK(ctx);
+        return CALZ_OK;
+    }
     if (m->layout == CALZ_LAYOUT_SELL_DICT) {
         const int64_t s0 = lo / 32, s1 = (hi + 31) / 32;
         const int64_t per_cta = (int64_t)(kSpmvThreads / 32) * kDictSlicesPerWarp;

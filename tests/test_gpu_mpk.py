@@ -95,6 +95,27 @@ def test_dictionary_coded_sell_is_bit_identical(name):
     assert relcols(outs["selld"][0], kernels.matrix_powers_newton(A, v, 5, lam, 1)) < TOL
 
 
+@pytest.mark.parametrize("name", ["poisson100", "lap3d"])
+def test_tma_staged_dictionary_kernel_is_bit_identical(name):
+    # opt-in variant: the x segments of a CTA's row block are bulk-copied into shared memory (cp.async.bulk + mbarrier)
+    A = MATS[name]()
+    n = A.shape[0]
+    v = np.cos(0.23 * np.arange(n)) + 0.7
+    lam = np.array([7.9, 0.1, 4.0, 6.0])
+    ctx = api.default_context()
+    dm = api.DeviceMatrix(A, 4, "selld")
+    assert dm.info("xs_rows") >= 512 and 1 <= dm.info("xs_groups") <= 3
+    V0 = api.matrix_powers_newton(dm, v, 4, lam, 1)
+    ctx.set_option("mpk_tma_x", 1)
+    try:
+        V1 = api.matrix_powers_newton(dm, v, 4, lam, 1)
+        M1 = api.matrix_powers_monomial(dm, v, 3)
+    finally:
+        ctx.set_option("mpk_tma_x", 0)
+    np.testing.assert_array_equal(V0, V1)
+    np.testing.assert_array_equal(M1, api.matrix_powers_monomial(dm, v, 3))
+
+
 def test_dictionary_coded_sell_falls_back_when_values_are_not_few():
     A = MATS["diag20000"]()                     # 20000 distinct values
     with pytest.raises(api.CalzError):
