@@ -456,4 +456,45 @@ int rmul_upper(calz_ctx* ctx, int c, const double* Rb, double* Rfin, const int* 
     return CALZ_OK;
 }
 
+// ------------------------------------------------------------------------------------------ fp64 DMMA peak probe
+// Register-resident mma.sync.m8n8k4.f64 chains (8 independent accumulators per warp): the denominator for "fraction of the
+// fp64 tensor pipe" of the Gram kernels (MEASURED_PEAKS.json has no fp64 figure).
+__global__ void __launch_bounds__(256) k_dmma_peak(double* out, int iters) {
+    double acc[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i][0] = acc[i][1] = 0.0;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dmma_8x8x4(acc[i][0], acc[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += acc[i][0] + acc[i][1];
+    if (s == 123.456) out[0] = s;          // keep the chain alive
+}
+
 }  // namespace calz
+
+extern "C" int calz_dmma_peak(calz_ctx* ctx, double* tflops) {
+    using namespace calz;
+    if (!ctx || !tflops) return CALZ_ERR_BADARG;
+    CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    double* d = nullptr;
+    CALZ_CUDA(ctx, cudaMalloc(&d, 64));
+    const int iters = 20000, grid = ctx->num_sms * 8;
+    cudaEvent_t e0, e1;
+    CALZ_CUDA(ctx, cudaEventCreate(&e0));
+    CALZ_CUDA(ctx, cudaEventCreate(&e1));
+    k_dmma_peak<<<grid, 256, 0, ctx->stream>>>(d, 100);
+    CALZ_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    k_dmma_peak<<<grid, 256, 0, ctx->stream>>>(d, iters);
+    CALZ_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    CALZ_CUDA(ctx, cudaEventSynchronize(e1));
+    float ms = 0;
+    CALZ_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = (double)grid * 8 /*warps*/ * iters * 8 /*chains*/ * 512.0;
+    *tflops = flops / (ms * 1e-3) / 1e12;
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    return CALZ_OK;
+}

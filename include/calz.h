@@ -177,6 +177,9 @@ int  calz_project_and_normalize_host(calz_ctx* ctx, int64_t n, int nblk, const d
  * project.m:34.  The fp64 DMMA tall-skinny contraction, exposed for the Gram roofline measurement. */
 int  calz_gram(calz_ctx* ctx, int64_t n, int m, const double* A, int64_t ldA, int c, const double* B,
                int64_t ldB, double* C_dev);
+/* measured peak of the fp64 tensor pipe (register-resident mma.sync.m8n8k4.f64 chains), TFLOP/s: the denominator of
+ * the Gram kernels' "fraction of the fp64 tensor pipe" */
+int  calz_dmma_peak(calz_ctx* ctx, double* tflops);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -87,12 +87,17 @@ def main():
     Y = torch.empty((s + 1, ld), dtype=torch.float64, device=dev)
     Cd = torch.zeros((64 * 64,), dtype=torch.float64, device=dev)
     torch.cuda.synchronize()
+    tf = C.c_double()
+    _lib.check(lib.calz_dmma_peak(ctx.h, C.byref(tf)), ctx.h)
+    print("  fp64 DMMA peak (register-resident m8n8k4 chains): %.1f TFLOP/s" % tf.value, flush=True)
     cases = [("gram c=%d" % s, lambda: lib.calz_gram(ctx.h, n, s, X.data_ptr(), ld, s, X.data_ptr(), ld, Cd.data_ptr()), 8 * n * s),
              ("gram c=%d" % (s + 1), lambda: lib.calz_gram(ctx.h, n, s + 1, Q.data_ptr(), ld, s + 1, Q.data_ptr(), ld, Cd.data_ptr()), 8 * n * (s + 1)),
              ("coeff Q'X M=%d c=%d" % (s + 1, s), lambda: lib.calz_gram(ctx.h, n, s + 1, Q.data_ptr(), ld, s, X.data_ptr(), ld, Cd.data_ptr()), 8 * n * (2 * s + 1))]
     for name, fn, nbytes in cases:
         ms = timed(fn)
-        print("  %-24s %8.3f ms  %7.1f GB/s = %.3f of peak" % (name, ms, nbytes / ms / 1e6, nbytes / ms / 1e6 / peak), flush=True)
+        mm, cc = (s, s) if name.startswith("gram c=%d" % s) and "c=%d" % (s + 1) not in name else ((s + 1, s + 1) if name.startswith("gram") else (s + 1, s))
+        print("  %-24s %8.3f ms  %7.1f GB/s = %.3f of HBM peak; %.2f TFLOP/s = %.3f of the DMMA peak" %
+              (name, ms, nbytes / ms / 1e6, nbytes / ms / 1e6 / peak, 2.0 * n * mm * cc / ms / 1e9, 2.0 * n * mm * cc / ms / 1e9 / tf.value), flush=True)
     R = np.zeros((s + 1, s + 1), order="F")
     info = C.c_int()
     for backend, name, c, nbytes in [("cholqr", "cholqr c=%d" % s, s, 24 * n * s), ("tsqr", "tsqr c=%d" % s, s, 16 * n * s),
