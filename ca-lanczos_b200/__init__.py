@@ -5,6 +5,7 @@ surface (same names and argument order as the MATLAB functions) backed by libcal
 synthetic inputs of SURVEY.md §8d; ``engine.BlockEngine`` is the device-resident block pipeline (needs torch).
 """
 from . import gallery  # noqa: F401
+from . import solver  # noqa: F401
 from .api import (  # noqa: F401
     CalzError, Context, DeviceMatrix, SpMV, cholqr, default_context, get_qr_backend, matrix_powers_monomial,
     matrix_powers_newton, normalize, project, projectAndNormalize, set_qr_backend, tsqr,

@@ -113,6 +113,20 @@ int calz_gram(calz_ctx* ctx, int64_t n, int m, const double* A, int64_t ldA, int
     return tsmm_tn(ctx, n, one_panel(A, ldA, m), B, ldB, c, C_dev, m, A == B && ldA == ldB && m == c, nullptr, 0, true);
 }
 
+int calz_block_axpy(calz_ctx* ctx, int64_t n, int m, const double* Q, int64_t ldQ, int c, const double* C_host, const double* X,
+                    int64_t ldX, double* Y, int64_t ldY) {
+    if (!ctx || !Q || !C_host || !Y || n < 1 || m < 1 || c < 1 || c > kMaxC)
+        return set_error(ctx, CALZ_ERR_BADARG, "calz_block_axpy: bad arguments");
+    CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    double* sm;
+    CALZ_TRY(small_scratch(ctx, (size_t)m * c, &sm));
+    // the coefficient block travels through pinned staging so that the copy is stream-ordered and the call stays asynchronous
+    CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // the staging area may still be read by an earlier copy
+    memcpy(ctx->pinned, C_host, (size_t)m * c * sizeof(double));
+    CALZ_CUDA(ctx, cudaMemcpyAsync(sm, ctx->pinned, (size_t)m * c * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    return ts_update(ctx, n, Q, ldQ, m, sm, m, X, X ? ldX : 0, c, Y, ldY, nullptr, 0);
+}
+
 int calz_cholqr(calz_ctx* ctx, int64_t n, int c, const double* X, int64_t ldX, double* Q, int64_t ldQ, double* R, int* info) {
     if (!ctx || !X || !Q || !R || n < 1 || c < 1 || c > kMaxC) return set_error(ctx, CALZ_ERR_BADARG, "calz_cholqr: bad arguments");
     CALZ_CUDA(ctx, cudaSetDevice(ctx->device));

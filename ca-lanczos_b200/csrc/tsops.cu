@@ -213,7 +213,7 @@ k_update(long long n, const double* __restrict__ Q, long long ldQ, int M, const 
         const bool ok = i < n;
         double y[CW];
 #pragma unroll
-        for (int j = 0; j < CW; ++j) y[j] = (ok && j < c) ? X[i + (long long)j * ldX] : 0.0;
+        for (int j = 0; j < CW; ++j) y[j] = (ok && j < c && X) ? X[i + (long long)j * ldX] : 0.0;
         for (int m0 = 0; m0 < M; m0 += MCH) {
             const int mm = min(MCH, M - m0);
             __syncthreads();

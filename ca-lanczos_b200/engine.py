@@ -63,6 +63,7 @@ class BlockEngine:
         self.T = None
         self.b = np.zeros(int(max_blocks) + 2)
         self.second = []
+        self._tmp = None
         # host landing zones for the small results
         self._R1 = np.zeros((s + 1, s), order="F")
         self._Rl = np.zeros((s, s), order="F")
@@ -81,13 +82,15 @@ class BlockEngine:
         return int(V.value), int(ldV.value)
 
     # ---- ca_lanczos.m:176-182
-    def first_block(self, q0):
-        """q0: host vector (owned rows), already normalised (ca_lanczos.m:55)."""
+    def first_block(self, q0, q_ptr=None):
+        """q0: host vector (owned rows), already normalised (ca_lanczos.m:55); or ``q_ptr``: the same on the device."""
         torch = self.torch
         s = self.s
-        q = torch.as_tensor(np.ascontiguousarray(q0, dtype=np.float64), device=self.Q.device)
-        torch.cuda.current_stream().synchronize()
-        V, ldV = self._mpk(q.data_ptr())
+        if q_ptr is None:
+            q = torch.as_tensor(np.ascontiguousarray(q0, dtype=np.float64), device=self.Q.device)
+            torch.cuda.current_stream().synchronize()
+            q_ptr = q.data_ptr()
+        V, ldV = self._mpk(q_ptr)
         rank = C.c_int()
         check(self.lib.calz_normalize(self.ctx.h, self.n, s + 1, C.c_void_p(V), ldV, _lib.QR[self.backend], 1e-8,
                                       C.c_void_p(self._qcol(0)), self.ld, self._Rfirst.ctypes.data_as(_lib.c_dp),
@@ -99,7 +102,7 @@ class BlockEngine:
         return Rk.copy()
 
     # ---- ca_lanczos.m:184-223 ('local')
-    def next_block(self, assemble_T: bool = True, events=None):
+    def next_block(self, assemble_T: bool = True, events=None, full_reorth: bool = False):
         """``events``: optional ((e0,e1,e2), stream) -- torch CUDA events recorded on libcalz' stream before the MPK,
         between MPK and projectAndNormalize, and after it (bench.py's per-phase timing)."""
         s = self.s
@@ -117,10 +120,22 @@ class BlockEngine:
         mc = (C.c_int * 1)(s + 1)
         rp = (_lib.c_dp * 1)(self._R1.ctypes.data_as(_lib.c_dp))
         second = C.c_int(); rank = C.c_int()
+        if full_reorth and self._tmp is None:
+            self._tmp = self.torch.zeros((s, self.ld), dtype=self.torch.float64, device=self.Q.device)
+            self.torch.cuda.synchronize(self.Q.device)
+        dst = self._tmp.data_ptr() if full_reorth else self._qcol((k - 1) * s + 1)
         check(self.lib.calz_project_and_normalize(self.ctx.h, self.n, 1, qblk, lds, mc, s, C.c_void_p(V + 8 * ldV), ldV,
-                                                  1, _lib.QR[self.backend], C.c_void_p(self._qcol((k - 1) * s + 1)),
+                                                  1, _lib.QR[self.backend], C.c_void_p(dst),
                                                   self.ld, rp, self._Rl.ctypes.data_as(_lib.c_dp), C.byref(second),
                                                   C.byref(rank)), self.ctx.h)
+        if full_reorth:
+            # 'fro' (ca_lanczos.m:193-197): orthogonalise the new block against ALL previous basis vectors as well;
+            # the coefficients of this second call are discarded, T is assembled from the first
+            qall = (C.c_void_p * 1)(self._qcol(0)); mall = (C.c_int * 1)((k - 1) * s + 1)
+            s2, r2 = C.c_int(), C.c_int()
+            check(self.lib.calz_project_and_normalize(self.ctx.h, self.n, 1, qall, lds, mall, s, C.c_void_p(dst), self.ld, 1,
+                                                      _lib.QR[self.backend], C.c_void_p(self._qcol((k - 1) * s + 1)), self.ld,
+                                                      None, None, C.byref(s2), C.byref(r2)), self.ctx.h)
         if events is not None:
             events[0][2].record(events[1])
         self.second.append(bool(second.value))

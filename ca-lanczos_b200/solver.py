@@ -1,0 +1,181 @@
+"""Device-resident drivers on top of the hot path: the CALLERS of the reference, so that
+a solve never moves an n-vector over PCIe.
+
+    T, Q = ca_lanczos(A, r, s, iter, basis, orth)          mirrors ca_lanczos.m:24 ('local' and 'full')
+
+Everything O(n) runs in libcalz kernels through the C ABI (SpMV, project, cholqr, block_axpy, the BlockEngine pipeline);
+torch only owns the device buffers.  The O(s^2) / O(s^3) host algebra follows the reference: the 2s-step Lanczos that
+produces the Newton shifts (ca_lanczos.m:66-72 -> lanczos.m:85-134), the modified Leja ordering with the running
+capacity rescale (modified_leja.m:24-196, real shifts), newton_basis_matrix.m:13-60, and the T assembly
+(ca_lanczos.m:200-223, in engine.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .api import Context, DeviceMatrix, default_context
+from .engine import BlockEngine
+
+
+# ----------------------------------------------------------------------------------------------- Leja / Newton basis
+def leja_order(x):
+    """Modified Leja ordering of REAL shifts, as leja.m:28-29 -> real_leja.m -> modified_leja.m computes it for the real
+    spectra of symmetric matrices: start from the point of largest modulus, then repeatedly take the point maximising
+    prod_j |x - y_j| / capacity, with the running capacity estimate and the rescale/unscale of the points
+    (modified_leja.m:95-117,:192).  Repeated shifts are an error there (x(1:n) overruns, real_leja.m:87) and here."""
+    x = np.sort(np.asarray(x, dtype=np.float64).ravel())
+    n = x.size
+    if n == 0:
+        return x
+    if np.any(np.diff(x) == 0):
+        raise IndexError("repeated shifts: the reference's real_leja/modified_leja indexes past the unique values")
+    x = x.copy()
+    out = [int(np.argmax(np.abs(x)))]
+    y = [x[out[0]]]
+    rest = [i for i in range(n) if i != out[0]]
+    capacity = 1.0
+    first = True
+    while rest:
+        npts = len(out)
+        if not first and npts > 1:
+            old = capacity
+            capacity = 1.0
+            for i in out[: npts - 1]:
+                capacity *= abs(y[npts - 1] - x[i]) ** (1.0 / npts)
+            scale = capacity / old
+            x = x / scale
+            y = [v / scale for v in y]
+        first = False
+        best, best_val = None, -1.0
+        for j in rest:
+            p = 1.0
+            for i in out:
+                p *= abs(x[j] - x[i]) / capacity
+            if p > best_val:
+                best, best_val = j, p
+        if best_val == 0.0 or np.isinf(best_val):
+            raise ValueError("Leja product under/overflowed")
+        rest.remove(best)
+        out.append(best)
+        y.append(x[best])
+    return np.asarray(y) * capacity
+
+
+def newton_basis_matrix(shifts, s):
+    """newton_basis_matrix.m:13-60 for real shifts: B(k,k) = shift_k, B(k+1,k) = 1."""
+    B = np.zeros((s + 1, s))
+    for k in range(s):
+        B[k, k] = shifts[k]
+        B[k + 1, k] = 1.0
+    return B
+
+
+# ----------------------------------------------------------------------------------------------- device helpers
+class _Dev:
+    """Thin wrappers: device pointers in, libcalz calls out (all on the context's stream)."""
+
+    def __init__(self, dm: DeviceMatrix):
+        import torch
+        self.torch, self.dm, self.ctx, self.lib = torch, dm, dm.ctx, dm.ctx.lib
+        self.n = dm.n
+        self.ld = (self.n + 31) // 32 * 32
+        self.dev = torch.device("cuda", self.ctx.device)
+
+    def zeros(self, cols):
+        t = self.torch.zeros((cols, self.ld), dtype=self.torch.float64, device=self.dev)
+        self.torch.cuda.synchronize(self.dev)
+        return t
+
+    def col(self, t, j):
+        return t.data_ptr() + 8 * self.ld * int(j)
+
+    def spmv(self, x_ptr, y_ptr):
+        check(self.lib.calz_spmv(self.dm.h, C.c_void_p(x_ptr), C.c_void_p(y_ptr)), self.ctx.h)
+
+    def axpy(self, q_ptr, m, coeff, x_ptr, y_ptr):
+        """y = x - Q*coeff  (Q n x m at q_ptr, coeff length m; one column)."""
+        cf = np.ascontiguousarray(coeff, dtype=np.float64).reshape(-1)
+        check(self.lib.calz_block_axpy(self.ctx.h, self.n, int(m), C.c_void_p(q_ptr), self.ld, 1, cf.ctypes.data_as(_lib.c_dp),
+                                       C.c_void_p(x_ptr) if x_ptr else None, self.ld, C.c_void_p(y_ptr), self.ld), self.ctx.h)
+
+    def project(self, q_ptr, m, x_ptr):
+        """coefficients = Q'x ; x -= Q*coefficients   (project.m:34-35 on one block); returns the coefficients."""
+        R = np.zeros((m, 1), order="F")
+        qb = (C.c_void_p * 1)(q_ptr); lds = (C.c_int64 * 1)(self.ld); mc = (C.c_int * 1)(int(m))
+        rp = (_lib.c_dp * 1)(R.ctypes.data_as(_lib.c_dp))
+        check(self.lib.calz_project(self.ctx.h, self.n, 1, qb, lds, mc, 1, C.c_void_p(x_ptr), self.ld, 0, rp), self.ctx.h)
+        return R[:, 0]
+
+    def normalize_col(self, x_ptr, q_ptr):
+        """q = x / sqrt(x'x); returns the norm  (cholqr.m on a single column == lanczos.m:109-110)."""
+        R = np.zeros((1, 1), order="F")
+        info = C.c_int()
+        check(self.lib.calz_cholqr(self.ctx.h, self.n, 1, C.c_void_p(x_ptr), self.ld, C.c_void_p(q_ptr), self.ld,
+                                   R.ctypes.data_as(_lib.c_dp), C.byref(info)), self.ctx.h)
+        return float(R[0, 0])
+
+
+def lanczos_T(dev: _Dev, q0_ptr, maxiter: int, orth: str = "local"):
+    """lanczos.m:85-134 (lanczos_basic, 'local' or 'fro'): the tridiagonal T of `maxiter` steps, vectors stay on the GPU."""
+    Qs = dev.zeros(maxiter + 2)
+    r = dev.col(Qs, maxiter + 1)
+    dev.torch.cuda.synchronize(dev.dev)
+    check(dev.lib.calz_block_axpy(dev.ctx.h, dev.n, 1, C.c_void_p(q0_ptr), dev.ld, 1, np.array([-1.0]).ctypes.data_as(_lib.c_dp),
+                                  None, dev.ld, C.c_void_p(dev.col(Qs, 0)), dev.ld), dev.ctx.h)        # Qs(:,1) = q0
+    alpha = np.zeros(maxiter); beta = np.zeros(maxiter)
+    for j in range(maxiter):
+        qj = dev.col(Qs, j)
+        dev.spmv(qj, r)                                                  # r = A*Q(:,j)                      (:103)
+        if j > 0:
+            dev.axpy(dev.col(Qs, j - 1), 1, [beta[j - 1]], r, r)         # r = r - beta(j-1)*Q(:,j-1)       (:105)
+        alpha[j] = dev.project(qj, 1, r)[0]                              # alpha = r'q ; r = r - alpha*q    (:107-108)
+        beta[j] = dev.normalize_col(r, dev.col(Qs, j + 1))               # beta = sqrt(r'r); q+ = r/beta    (:109-110)
+        if orth in ("full", "fro"):
+            dev.project(dev.col(Qs, 0), j + 1, dev.col(Qs, j + 1))       # one CGS sweep, no renormalisation (:62-66)
+    return np.diag(alpha) + np.diag(beta[: maxiter - 1], 1) + np.diag(beta[: maxiter - 1], -1)
+
+
+def newton_shifts(dm: DeviceMatrix, q0_ptr, s: int, orth: str = "full"):
+    """ca_lanczos.m:66-71: 2s-step Lanczos, eig, Leja order; returns all 2s ordered shifts (the first s are used)."""
+    dev = _Dev(dm)
+    T = lanczos_T(dev, q0_ptr, 2 * s, orth)
+    return leja_order(np.linalg.eigvalsh(T))
+
+
+# ----------------------------------------------------------------------------------------------- ca_lanczos
+def ca_lanczos(A, r, s, iter, basis="newton", orth="local", backend="cholqr2", ctx: Context | None = None, shifts=None,
+               return_engine=False):
+    """ca_lanczos.m:24-86 with ca_lanczos_basic (:150-245), device resident.  ``A``: scipy sparse or DeviceMatrix;
+    ``r``: host start vector (owned rows).  Returns (T, Q) like the reference (Q as a host array), or the engine."""
+    orth = str(orth).lower()
+    if orth not in ("local", "full"):
+        raise NotImplementedError("orth=%s: only 'local' and 'full' are on the hot path" % orth)
+    if basis.lower() not in ("monomial", "newton"):
+        raise ValueError("ERROR: Unknown basis type: " + basis)
+    s = int(s)
+    t = int(np.ceil(iter / s))                                                        # :52
+    dm = A if isinstance(A, DeviceMatrix) else DeviceMatrix(A, s_max=max(s, 1), ctx=ctx or default_context())
+    dev = _Dev(dm)
+    import torch
+    rq = torch.as_tensor(np.ascontiguousarray(r, dtype=np.float64), device=dev.dev)
+    buf = dev.zeros(2)
+    buf[0, : dev.n] = rq
+    torch.cuda.synchronize(dev.dev)
+    dev.normalize_col(dev.col(buf, 0), dev.col(buf, 1))                               # q = r/sqrt(r'*r)   (:55)
+    q_ptr = dev.col(buf, 1)
+    if basis.lower() == "newton" and shifts is None:
+        shifts = newton_shifts(dm, q_ptr, s, "full")                                  # :68-70
+    eng = BlockEngine(dm, s, t + 1, basis, shifts, backend)
+    eng.first_block(None, q_ptr=q_ptr)
+    if orth == "local":
+        eng.run_blocks(t - 1)
+    else:
+        for _ in range(t - 1):
+            eng.next_block(full_reorth=True)
+    if return_engine:
+        return eng
+    return eng.T_matrix(), eng.Q_host()

@@ -177,6 +177,11 @@ int  calz_project_and_normalize_host(calz_ctx* ctx, int64_t n, int nblk, const d
  * project.m:34.  The fp64 DMMA tall-skinny contraction, exposed for the Gram roofline measurement. */
 int  calz_gram(calz_ctx* ctx, int64_t n, int m, const double* A, int64_t ldA, int c, const double* B,
                int64_t ldB, double* C_dev);
+/* Y = X - Q*C  (Q n x m, C m x c on the HOST, X n x c or NULL for zero; Y may alias X).  The tall-skinny update of
+ * project.m:35, exposed for the callers' own O(n) work: the three-term recurrence of lanczos.m:103-110 and the Ritz
+ * vector assembly Q*Vp of restarted_ca_lanczos.m:135-139 / ca_lanczos.m:94 (pass C = -Vp, X = NULL). */
+int  calz_block_axpy(calz_ctx* ctx, int64_t n, int m, const double* Q, int64_t ldQ, int c, const double* C_host,
+                     const double* X, int64_t ldX, double* Y, int64_t ldY);
 /* measured peak of the fp64 tensor pipe (register-resident mma.sync.m8n8k4.f64 chains), TFLOP/s: the denominator of
  * the Gram kernels' "fraction of the fp64 tensor pipe" */
 int  calz_dmma_peak(calz_ctx* ctx, double* tflops);

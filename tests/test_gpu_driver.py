@@ -133,3 +133,54 @@ def test_driver_against_committed_goldens(name):
     tol = 1e-10 if str(g["basis"]) == "newton" else 1e-8
     assert np.max(np.abs(T - g["T"])) <= tol * np.max(np.abs(g["T"]))
     assert np.max(np.abs(Q[g["rows"]][:, : s + 1] - g["Q_rows"][:, : s + 1])) < 1e-9
+
+
+# ----------------------------------------------------------------------------- device-resident drivers (N1, N3, N4)
+from ca_lanczos_b200 import solver  # noqa: E402
+
+
+def test_leja_order_matches_oracle_restatement():
+    from oracle import leja
+    x = np.array([0.3, 11.2, 5.5, 7.9, 2.2, 9.4, 1.1, 4.4, 10.1, 6.3])
+    y, _ = leja.leja(x, "nonmodified")
+    np.testing.assert_allclose(solver.leja_order(x), y, rtol=1e-14)
+    with pytest.raises(IndexError):
+        solver.leja_order([1.0, 2.0, 2.0])
+
+
+@pytest.mark.parametrize("orth", ["local", "full"])
+def test_device_shift_generation_matches_oracle(orth):
+    # ca_lanczos.m:66-71 on the device: 2s-step Lanczos -> eig -> Leja; generic start vector (no Leja ties)
+    A = gallery.laplace3d(20, 18, 16)
+    n, s = A.shape[0], 6
+    r = _start(n, "generic"); q = r / np.sqrt(r @ r)
+    To, _ = drivers.lanczos(A, q, 2 * s, orth)
+    import torch
+    dm = api.DeviceMatrix(A, s_max=s)
+    qd = torch.as_tensor(q, device="cuda")
+    torch.cuda.synchronize()
+    dev = solver._Dev(dm)
+    Tg = solver.lanczos_T(dev, qd.data_ptr(), 2 * s, orth)
+    assert np.max(np.abs(Tg - To)) <= 1e-10 * np.max(np.abs(To))
+    from oracle import leja
+    so, _ = leja.leja(np.linalg.eigvalsh(To), "nonmodified")
+    np.testing.assert_allclose(solver.newton_shifts(dm, qd.data_ptr(), s, orth), so, rtol=1e-8)
+
+
+@pytest.mark.parametrize("cfg", [("lap3d", 8, 40, "newton", "local"), ("lap3d", 8, 40, "newton", "full"),
+                                 ("poisson", 4, 40, "monomial", "local"), ("diag", 8, 48, "newton", "full")])
+def test_device_resident_ca_lanczos_matches_reference_driver(cfg):
+    # the whole of ca_lanczos.m:24-245 with no n-vector crossing PCIe, against the restated driver with oracle kernels
+    name, s, iters, basis, orth = cfg
+    A = {"poisson": lambda: gallery.poisson2d(60), "diag": lambda: gallery.diag_linspace(6000, 100.0),
+         "lap3d": lambda: gallery.laplace3d(24, 20, 22)}[name]()
+    r = _start(A.shape[0], "generic")
+    To, Qo = drivers.ca_lanczos(A, r, s, iters, basis, orth)
+    Tg, Qg = solver.ca_lanczos(A, r, s, iters, basis, orth, backend="tsqr")
+    assert Tg.shape == To.shape and Qg.shape == Qo.shape
+    tol = 1e-10 if basis == "newton" else 1e-8
+    assert np.max(np.abs(Tg - To)) <= tol * np.max(np.abs(To))
+    np.testing.assert_allclose(ritz(Tg)[:4], ritz(To)[:4], rtol=1e-8)
+    assert orth_loss(Qg) <= max(10 * orth_loss(Qo), 1e-9)
+    if orth == "full":
+        assert orth_loss(Qg) < 1e-12
