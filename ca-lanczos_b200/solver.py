@@ -179,3 +179,32 @@ def ca_lanczos(A, r, s, iter, basis="newton", orth="local", backend="cholqr2", c
     if return_engine:
         return eng
     return eng.T_matrix(), eng.Q_host()
+
+
+# ----------------------------------------------------------------------------------------------- Ritz pairs (N1, N2)
+def ritz_residuals(eng: BlockEngine, nev: int | None = None):
+    """compute_ritz_rnorm of ca_lanczos.m:88-97 on the device: Ritz values of T (general eig, T is not exactly
+    symmetric), Ritz vectors x = Q*Vp(:,i) (tall-skinny GEMM, N1) and relative residuals ||A x - l x|| / ||l x|| (N2),
+    sorted by descending Ritz value.  Returns (values, residuals)."""
+    T = eng.T_matrix()
+    m = T.shape[0]
+    lam, Vp = np.linalg.eig(T)
+    lam, Vp = np.real(lam), np.real(Vp)
+    order = np.argsort(-lam, kind="stable")
+    nev = m if nev is None else min(int(nev), m)
+    dev = _Dev(eng.dm)
+    buf = dev.zeros(4)
+    x, ax, rr, tmp = (dev.col(buf, j) for j in range(4))
+    vals, res = [], []
+    for i in order[:nev]:
+        l = float(lam[i])
+        cf = np.ascontiguousarray(-Vp[:, i])
+        check(dev.lib.calz_block_axpy(dev.ctx.h, dev.n, m, C.c_void_p(eng._qcol(0)), eng.ld, 1, cf.ctypes.data_as(_lib.c_dp),
+                                      None, dev.ld, C.c_void_p(x), dev.ld), dev.ctx.h)          # x = Q*Vp(:,i)
+        dev.spmv(x, ax)
+        dev.axpy(x, 1, [l], ax, rr)                                                                # A*x - l*x
+        nr = dev.normalize_col(rr, tmp)
+        nx = dev.normalize_col(x, tmp)
+        vals.append(l)
+        res.append(nr / (abs(l) * nx))
+    return np.asarray(vals), np.asarray(res)

@@ -184,3 +184,20 @@ def test_device_resident_ca_lanczos_matches_reference_driver(cfg):
     assert orth_loss(Qg) <= max(10 * orth_loss(Qo), 1e-9)
     if orth == "full":
         assert orth_loss(Qg) < 1e-12
+
+
+def test_ritz_vectors_and_residuals_on_device():
+    # ca_lanczos.m:88-97 (compute_ritz_rnorm): x = Q*Vp(:,i), ||A x - l x|| / ||l x||, against numpy on the host copies
+    A = gallery.diag_linspace(5000, 100.0)
+    r = np.ones(5000)
+    eng = solver.ca_lanczos(A, r, 8, 160, "newton", "full", backend="tsqr", return_engine=True)
+    vals, res = solver.ritz_residuals(eng, nev=5)
+    T, Q = eng.T_matrix(), eng.Q_host()
+    lam, Vp = np.linalg.eig(T)
+    order = np.argsort(-lam.real, kind="stable")
+    for k, i in enumerate(order[:5]):
+        x = Q @ Vp[:, i].real
+        ref = np.linalg.norm(A @ x - lam[i].real * x) / np.linalg.norm(lam[i].real * x)
+        assert vals[k] == pytest.approx(lam[i].real, rel=1e-14)
+        assert res[k] == pytest.approx(ref, rel=1e-6, abs=1e-13)
+    assert res[0] < 1e-3 and vals[0] == pytest.approx(100.0, rel=1e-6)       # the top Ritz pair is converging
