@@ -393,11 +393,28 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
             for (int64_t r = sl * C; r < std::min<int64_t>(n_loc, sl * C + C); ++r)
                 for (int32_t j = 0; j < rowlen[r]; ++j)
                     packed[((size_t)(slice_ptr[sl] + j / 8) * 32 + (size_t)(r - sl * C)) * 8 + (j % 8)] = codes[h_rowptr[r] + j];
+        // how often do the 32 lanes of a (block, slot) hold ONE code?  (sampled)  A warp-uniform code is a broadcast read
+        // from the constant bank; divergent codes would serialise there, so ragged matrices keep the dictionary in shared memory
+        {
+            int64_t uni = 0, tot = 0;
+            const int64_t step = std::max<int64_t>(1, blocks / 4096) | 1;     // odd: visits every residue of a power-of-two period
+            for (int64_t b = 0; b < blocks; b += step)
+                for (int q = 0; q < 8; ++q) {
+                    const uint8_t* pb = packed.data() + (size_t)b * 256 + q;
+                    bool same = true;
+                    for (int l = 1; l < 32 && same; ++l) same = pb[l * 8] == pb[0];
+                    uni += same;
+                    ++tot;
+                }
+            m->dict_uniform = tot ? (double)uni / (double)tot : 0.0;
+        }
         std::vector<double> dict(2 * 256, 0.0);                                   // {value, offset-as-int64 bits} pairs, 16 B each
         for (size_t k = 0; k < dict_val.size(); ++k) {
             dict[2 * k] = dict_val[k];
             long long o = dict_off[k];
             memcpy(&dict[2 * k + 1], &o, 8);
+            m->h_dict->v[k] = dict_val[k];
+            m->h_dict->offb[k] = (int)(o * 8);
         }
         m->sell_padded = blocks * 256;
         m->dict_size = (int)dict_val.size();
@@ -536,6 +553,7 @@ int calz_mat_info(const calz_mat* m, const char* what, int64_t* value) {
     else if (!strcmp(what, "s_max")) *value = m->s_max;
     else if (!strcmp(what, "ldW")) *value = m->ldW;
     else if (!strcmp(what, "dict_size")) *value = m->dict_size;
+    else if (!strcmp(what, "dict_uniform_pct")) *value = (int64_t)(100.0 * m->dict_uniform);
     else if (!strcmp(what, "xs_rows")) *value = m->xs_rows;
     else if (!strcmp(what, "xs_groups")) *value = m->xs_groups;
     else if (!strcmp(what, "p2p_halo")) *value = m->p2p_halo ? 1 : 0;

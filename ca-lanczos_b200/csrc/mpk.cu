@@ -58,64 +58,139 @@ k_spmv_sell(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ c
 }
 
 // ---- dictionary-coded SELL: one warp per slice, one lane per row; each lane pulls 8 code bytes per 64-bit load and looks
-//      {value, column offset} up in a 4 KB dictionary that lives in L1.  Same summation order as CSR/SELL (bit-identical).
+//      {value, column offset} up in a <= 4 KB dictionary.  Same summation order as CSR/SELL (bit-identical).
+//      Where the dictionary lives is a template parameter (all three measured on B200):
+//        DM_SHARED  : split value / byte-offset arrays in shared memory (LDS.64 + LDS.32 per non-zero): 0.137 ms per C3 SpMV
+//        DM_CONST   : kernel parameter = constant bank (LDC): a warp-uniform code costs no L1 data-pipe wavefront, 0.121 ms
+//      (one 16-byte shared entry read with LDS.128 was measured too: 0.131 ms, dropped)
 constexpr int kDictSlicesPerWarp = 2;     // independent slices per warp: the loads of both are in flight together
+enum { DM_SHARED = 0, DM_CONST = 2 };
 
-template <bool NEWTON>
-__global__ void __launch_bounds__(kSpmvThreads)
-k_spmv_selld(const int32_t* __restrict__ slice_ptr, const uint2* __restrict__ codes, const double2* __restrict__ dict, int dict_size,
-             const double* __restrict__ x, const double* __restrict__ xprev, double* __restrict__ y, int64_t slice_lo,
-             int64_t slice_hi, int64_t n_loc, double shift, double pair) {
-    constexpr int NS = kDictSlicesPerWarp;
-    // dictionary in shared memory, split into values and 32-bit offsets (broadcast / conflict-light reads)
-    __shared__ double sval[256];
-    __shared__ int soff[256];
+struct DictParam {                        // 3 KB, passed by value as a __grid_constant__ kernel parameter
+    double v[256];
+    int offb[256];                        // column offset pre-scaled to bytes
+};
+
+template <int DM>
+__device__ __forceinline__ uint32_t dict_stage(unsigned char* sraw, const DictParam& P) {
+    if (DM == DM_CONST) return 0;
+    uint32_t sbase;
+    {   // opaque copy: keeps the base in a register instead of re-deriving it (S2R + LEA) at every use
+        const uint32_t t = (uint32_t)__cvta_generic_to_shared(sraw);
+        asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(t));
+    }
     for (int i = threadIdx.x; i < 256; i += kSpmvThreads) {
-        const double2 e = i < dict_size ? __ldg(dict + i) : make_double2(0.0, 0.0);
-        sval[i] = e.x;
-        soff[i] = (int)__double_as_longlong(e.y);
+        *reinterpret_cast<double*>(sraw + 8 * i) = P.v[i];
+        *reinterpret_cast<int*>(sraw + 2048 + 4 * i) = P.offb[i];
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
-    const int64_t slice0 = slice_lo + ((int64_t)blockIdx.x * (kSpmvThreads / 32) + (threadIdx.x >> 5)) * NS;
-    if (slice0 >= slice_hi) return;
-    int32_t p0[NS], nb[NS];
-    int maxb = 0;
+    return sbase;
+}
+
+// the 8 non-zeros of one code word pair, ascending column order.  `sbase` is the 4 KB-aligned shared-window address of the
+// dictionary, so an entry address is one LOP3: (bits & mask) | sbase.
+template <int DM, int NS>
+__device__ __forceinline__ void dict_fma8(const DictParam& P, uint32_t sbase, const uint2 (&w)[NS], const char* const (&xr)[NS],
+                                          double (&sum)[NS]) {
 #pragma unroll
-    for (int i = 0; i < NS; ++i) {
-        const bool ok = slice0 + i < slice_hi;
-        p0[i] = ok ? __ldg(slice_ptr + slice0 + i) : 0;
-        nb[i] = ok ? __ldg(slice_ptr + slice0 + i + 1) - p0[i] : 0;
-        maxb = max(maxb, nb[i]);
-    }
-    double sum[NS];
-    int row[NS];
+    for (int q = 0; q < 8; ++q) {
 #pragma unroll
-    for (int i = 0; i < NS; ++i) {
-        sum[i] = 0.0;
-        row[i] = (int)min((slice0 + i) * 32 + lane, n_loc - 1);
-    }
-    for (int b = 0; b < maxb; ++b) {
-        uint2 w[NS];
-#pragma unroll
-        for (int i = 0; i < NS; ++i) w[i] = (b < nb[i]) ? __ldg(codes + (int64_t)(p0[i] + b) * 32 + lane) : make_uint2(~0u, ~0u);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-#pragma unroll
-            for (int i = 0; i < NS; ++i) {
-                const unsigned int half = q < 4 ? w[i].x : w[i].y;
-                const unsigned int c = (half >> (8 * (q & 3))) & 0xffu;
-                if (c != 255u) sum[i] = fma(sval[c], x[row[i] + soff[c]], sum[i]);
+        for (int i = 0; i < NS; ++i) {
+            const unsigned int half = q < 4 ? w[i].x : w[i].y;
+            const unsigned int c = (half >> (8 * (q & 3))) & 0xffu;
+            if (c != 255u) {
+                double v;
+                int ob;
+                if (DM == DM_CONST) {
+                    v = P.v[c];
+                    ob = P.offb[c];
+                } else {
+                    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((c << 3) | sbase));
+                    asm volatile("ld.shared.s32 %0, [%1+2048];" : "=r"(ob) : "r"((c << 2) | sbase));
+                }
+                sum[i] = fma(v, *reinterpret_cast<const double*>(xr[i] + ob), sum[i]);
             }
         }
     }
+}
+
+// PERSIST: an occupancy-sized grid, every warp strides over work items of NS slices, and the dependent chain
+// slice_ptr -> codes -> x is software pipelined (the slice pointers of item i+2 and the code words of item i+1 are in flight
+// while the x gathers of item i are issued).  !PERSIST: one work item per warp.
+template <bool NEWTON, bool PERSIST, int DM>
+__global__ void __launch_bounds__(kSpmvThreads, 5)
+k_spmv_selld(const int32_t* __restrict__ slice_ptr, const uint2* __restrict__ codes, const __grid_constant__ DictParam P,
+             const double* __restrict__ x, const double* __restrict__ xprev, double* __restrict__ y, int64_t slice_lo,
+             int64_t slice_hi, int64_t n_loc, double shift, double pair) {
+    constexpr int NS = kDictSlicesPerWarp;
+    __shared__ __align__(4096) unsigned char sraw[DM == DM_CONST ? 16 : 4096];
+    const int lane = threadIdx.x & 31;
+    const int64_t items = (slice_hi - slice_lo + NS - 1) / NS;
+    const int64_t stride = PERSIST ? (int64_t)gridDim.x * (kSpmvThreads / 32) : items;
+    int64_t it = (int64_t)blockIdx.x * (kSpmvThreads / 32) + (threadIdx.x >> 5);
+    // prologue: pointers of items it and it+stride, code words of item it
+    int32_t p0[NS], nb[NS], p0n[NS], nbn[NS];
+    uint2 w[NS];
 #pragma unroll
     for (int i = 0; i < NS; ++i) {
-        const int64_t r = (slice0 + i) * 32 + lane;
-        if (slice0 + i < slice_hi && r < n_loc) {
-            double v = sum[i];
-            if (NEWTON) v = newton_epilogue(v, x[r], pair != 0.0 ? xprev[r] : 0.0, shift, pair);
-            y[r] = v;
+        const int64_t sa = slice_lo + it * NS + i, sb = slice_lo + (it + stride) * NS + i;
+        const bool oka = it < items && sa < slice_hi, okb = PERSIST && it + stride < items && sb < slice_hi;
+        p0[i] = oka ? __ldg(slice_ptr + sa) : 0;
+        nb[i] = oka ? __ldg(slice_ptr + sa + 1) - p0[i] : 0;
+        p0n[i] = okb ? __ldg(slice_ptr + sb) : 0;
+        nbn[i] = okb ? __ldg(slice_ptr + sb + 1) - p0n[i] : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < NS; ++i) w[i] = nb[i] > 0 ? __ldg(codes + (int64_t)p0[i] * 32 + lane) : make_uint2(~0u, ~0u);
+    const uint32_t sbase = dict_stage<DM>(sraw, P);
+    for (; it < items; it += stride) {
+        uint2 wn[NS];
+        int32_t p0nn[NS], nbnn[NS];
+        if (PERSIST) {   // prefetch: code words of the next item, slice pointers of the one after
+#pragma unroll
+            for (int i = 0; i < NS; ++i) wn[i] = nbn[i] > 0 ? __ldg(codes + (int64_t)p0n[i] * 32 + lane) : make_uint2(~0u, ~0u);
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                const int64_t sc = slice_lo + (it + 2 * stride) * NS + i;
+                const bool okc = it + 2 * stride < items && sc < slice_hi;
+                p0nn[i] = okc ? __ldg(slice_ptr + sc) : 0;
+                nbnn[i] = okc ? __ldg(slice_ptr + sc + 1) - p0nn[i] : 0;
+            }
+        }
+        const int64_t slice0 = slice_lo + it * NS;
+        double sum[NS];
+        const char* xr[NS];
+        int maxb = 0;
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            sum[i] = 0.0;
+            xr[i] = reinterpret_cast<const char*>(x + min((slice0 + i) * 32 + lane, n_loc - 1));
+            maxb = max(maxb, nb[i]);
+        }
+        for (int b = 0; b < maxb; ++b) {
+            if (b > 0) {
+#pragma unroll
+                for (int i = 0; i < NS; ++i)
+                    w[i] = (b < nb[i]) ? __ldg(codes + (int64_t)(p0[i] + b) * 32 + lane) : make_uint2(~0u, ~0u);
+            }
+            dict_fma8<DM, NS>(P, sbase, w, xr, sum);
+        }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) {
+            const int64_t r = (slice0 + i) * 32 + lane;
+            if (slice0 + i < slice_hi && r < n_loc) {
+                double v = sum[i];
+                if (NEWTON) v = newton_epilogue(v, x[r], pair != 0.0 ? xprev[r] : 0.0, shift, pair);
+                y[r] = v;
+            }
+        }
+        if (PERSIST) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                w[i] = wn[i];
+                p0[i] = p0n[i]; nb[i] = nbn[i];
+                p0n[i] = p0nn[i]; nbn[i] = nbnn[i];
+            }
         }
     }
 }
@@ -269,6 +344,44 @@ int launch_csr(calz_mat* m, const double* x, const double* xp, double* y, int64_
     return CALZ_OK;
 }
 
+template <bool NEWTON, bool PERSIST, int DM>
+int launch_selld_t(calz_mat* m, const double* x, const double* xp, double* y, int64_t s0, int64_t s1, double shift, double pair) {
+    calz_ctx* ctx = m->ctx;
+    const int64_t per_cta = (int64_t)(kSpmvThreads / 32) * kDictSlicesPerWarp;
+    unsigned grid = (unsigned)((s1 - s0 + per_cta - 1) / per_cta);
+    if (PERSIST) {
+        static int occ = 0;
+        if (!occ) {
+            CALZ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_selld<NEWTON, PERSIST, DM>, kSpmvThreads, 0));
+            if (occ < 1) occ = 1;
+        }
+        const unsigned cap = (unsigned)(ctx->num_sms * occ);
+        if (grid > cap) grid = cap;
+    }
+    k_spmv_selld<NEWTON, PERSIST, DM><<<grid, kSpmvThreads, 0, ctx->stream>>>(m->d_slice_ptr, (const uint2*)m->d_codes, *(const DictParam*)m->h_dict,
+                                                                             x, xp, y, s0, s1, m->n_loc, shift, pair);
+    CALZ_LAUNCH_CHECK(ctx);
+    return CALZ_OK;
+}
+
+int launch_selld(calz_mat* m, const double* x, const double* xp, double* y, int64_t lo, int64_t hi, bool newton, double shift, double pair) {
+    calz_ctx* ctx = m->ctx;
+    static_assert(sizeof(DictParam) == sizeof(m->h_dict), "dictionary parameter block");
+    const int64_t s0 = lo / 32, s1 = (hi + 31) / 32;
+    int dm = (int)ctx->opt_mpk_dict_mode;
+    if (dm < 0) dm = m->dict_uniform >= 0.75 ? DM_CONST : DM_SHARED;
+    const int key = (newton ? 1 : 0) | (ctx->opt_mpk_persist ? 2 : 0) | (dm << 2);
+    if (!newton) { shift = 0.0; pair = 0.0; }
+#define CALZ_SELLD_CASE(NW, PS, DM) \
+    case ((NW) | ((PS) << 1) | ((DM) << 2)): return launch_selld_t<NW != 0, PS != 0, DM>(m, x, xp, y, s0, s1, shift, pair);
+    switch (key) {
+        CALZ_SELLD_CASE(0, 0, 0) CALZ_SELLD_CASE(1, 0, 0) CALZ_SELLD_CASE(0, 1, 0) CALZ_SELLD_CASE(1, 1, 0)
+        CALZ_SELLD_CASE(0, 0, 2) CALZ_SELLD_CASE(1, 0, 2) CALZ_SELLD_CASE(0, 1, 2) CALZ_SELLD_CASE(1, 1, 2)
+        default: return set_error(ctx, CALZ_ERR_BADARG, "mpk_dict_mode must be -1 (auto), 0 (shared) or 2 (constant bank)");
+    }
+#undef CALZ_SELLD_CASE
+}
+
 // one SpMV step on local rows [lo,hi) (already aligned to the layout granule)
 int spmv_step(calz_mat* m, const double* x, const double* xp, double* y, int64_t lo, int64_t hi, bool newton,
               double shift, double pair) {
@@ -296,19 +409,7 @@ int spmv_step(calz_mat* m, const double* x, const double* xp, double* y, int64_t
         CALZ_LAUNCH_CHECK(ctx);
         return CALZ_OK;
     }
-    if (m->layout == CALZ_LAYOUT_SELL_DICT) {
-        const int64_t s0 = lo / 32, s1 = (hi + 31) / 32;
-        const int64_t per_cta = (int64_t)(kSpmvThreads / 32) * kDictSlicesPerWarp;
-        const unsigned grid = (unsigned)((s1 - s0 + per_cta - 1) / per_cta);
-        const uint2* codes = (const uint2*)m->d_codes;
-        const double2* dict = (const double2*)m->d_dict;
-        if (newton)
-            k_spmv_selld<true><<<grid, kSpmvThreads, 0, ctx->stream>>>(m->d_slice_ptr, codes, dict, m->dict_size, x, xp, y, s0, s1, m->n_loc, shift, pair);
-        else
-            k_spmv_selld<false><<<grid, kSpmvThreads, 0, ctx->stream>>>(m->d_slice_ptr, codes, dict, m->dict_size, x, xp, y, s0, s1, m->n_loc, 0.0, 0.0);
-        CALZ_LAUNCH_CHECK(ctx);
-        return CALZ_OK;
-    }
+    if (m->layout == CALZ_LAYOUT_SELL_DICT) return launch_selld(m, x, xp, y, lo, hi, newton, shift, pair);
     if (m->layout == CALZ_LAYOUT_SELL) {
         const int64_t s0 = lo / 32, s1 = (hi + 31) / 32;
         const unsigned grid = (unsigned)((s1 - s0 + kSpmvThreads / 32 - 1) / (kSpmvThreads / 32));

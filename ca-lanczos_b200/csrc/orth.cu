@@ -253,6 +253,7 @@ static int pan_enqueue(calz_ctx* ctx, int64_t n, int nblk, const double* const* 
     // fused tile pipeline (tiles.cu): one previous block, Cholesky-based QR, TMA-compatible alignment
     const bool tiled = nb == 1 && fuse_norms && ctx->opt_tile_pipeline &&
                        tile_path_ok(n, Qblk[blocks[0]], ldQ[blocks[0]], mcols[blocks[0]], X, ldX, c, QZ, ldQZ);
+    const bool fused_solve = tiled && backend != CALZ_QR_TSQR && ctx->opt_pan_fused_solve;
     size_t doubles = 8;                                // flags
     std::vector<size_t> off1(nb), off2(nb);
     std::vector<int> ld1(nb), ld2(nb);
@@ -285,20 +286,28 @@ static int pan_enqueue(calz_ctx* ctx, int64_t n, int nblk, const double* const* 
         double *S1 = sm + off1[0], *S2 = sm + off2[0], *S3 = sm + offS3;
         // pass 1: S1 = [Q X]'X  -> C1 and ||x_i||^2
         CALZ_TRY(tile_pass(ctx, 0, n, Qblk[i], ldQ[i], m, X, ldX, c, nullptr, 0, nullptr, 0, S1, ldS, nullptr, 0, true));
-        // pass 2: Y = X - Q*C1 (into QZ), S2 = [Q Y]'Y -> C2 (used only if pass 2 of the reference fires) and G_Y
-        CALZ_TRY(tile_pass(ctx, 1, n, Qblk[i], ldQ[i], m, X, ldX, c, S1, ldS, QZ, ldQZ, S2, ldS, nullptr, 0, true));
-        if (backend != CALZ_QR_TSQR)
-            CALZ_TRY(chol_small(ctx, c, S2 + m, R1, flags + 1, S1 + m, ldS + 1, flags + 0, nullptr, 0, backend == CALZ_QR_CHOLQR2,
-                                backend == CALZ_QR_CHOLQR2 ? flags + 3 : nullptr, ldS));
-        else   // TSQR: the norms-after of the test are sqrt(diag(Y'Y)); Y itself is only factorised if pass 2 does not fire
-            CALZ_TRY(norm_drop_from_gram(ctx, c, S2 + m, ldS, S1 + m, ldS + 1, flags + 0));
-        // pass 3 (iff the norm-drop test fired): Z = Y - Q*C2 in place, S3 = Z'Z
-        CALZ_TRY(tile_pass(ctx, 2, n, Qblk[i], ldQ[i], m, QZ, ldQZ, c, S2, ldS, QZ, ldQZ, S3, ldS, flags, 1, true));
-        if (backend != CALZ_QR_TSQR)
-            CALZ_TRY(chol_small(ctx, c, S3 + m, R2, flags + 2, nullptr, 0, nullptr, flags, 1, backend == CALZ_QR_CHOLQR2,
-                                backend == CALZ_QR_CHOLQR2 ? flags + 4 : nullptr, ldS));
-        else   // one Householder TSQR of whatever QZ holds now (Z, or Y if pass 2 did not fire): the LAST normalize
-            CALZ_TRY(tsqr_factor(ctx, n, c, QZ, ldQZ, R1, nullptr, 0));
+        // pass 2: Y = X - Q*C1 (into QZ), S2 = [Q Y]'Y -> C2 (used only if pass 2 of the reference fires) and G_Y.
+        // Cholesky back ends (fused_solve): Y stays in registers / shared memory, it is never written to HBM
+        CALZ_TRY(tile_pass(ctx, 1, n, Qblk[i], ldQ[i], m, X, ldX, c, S1, ldS, fused_solve ? nullptr : QZ, ldQZ, S2, ldS, nullptr, 0, true));
+        if (fused_solve) {
+            // R1, the norm-drop test, R2 from the downdated Gram and Rf in one launch; then ONE more pass over [Q | X]:
+            // QZ = ((X - Q*C1) - Q*C2)/Rf if the test fired (pass 3 and the triangular solve fused), else QZ = (X - Q*C1)/Rf
+            CALZ_TRY(chol_pan(ctx, c, m, S2, ldS, S1 + m, ldS + 1, backend == CALZ_QR_CHOLQR2, R1, R2, Rf, flags));
+            CALZ_TRY(tile_update_solve(ctx, n, Qblk[i], ldQ[i], m, X, ldX, c, S1, ldS, S2, ldS, flags, Rf, QZ, ldQZ));
+        } else {
+            if (backend != CALZ_QR_TSQR)
+                CALZ_TRY(chol_small(ctx, c, S2 + m, R1, flags + 1, S1 + m, ldS + 1, flags + 0, nullptr, 0, backend == CALZ_QR_CHOLQR2,
+                                    backend == CALZ_QR_CHOLQR2 ? flags + 3 : nullptr, ldS));
+            else   // TSQR: the norms-after of the test are sqrt(diag(Y'Y)); Y itself is only factorised if pass 2 does not fire
+                CALZ_TRY(norm_drop_from_gram(ctx, c, S2 + m, ldS, S1 + m, ldS + 1, flags + 0));
+            // pass 3 (iff the norm-drop test fired): Z = Y - Q*C2 in place, S3 = Z'Z
+            CALZ_TRY(tile_pass(ctx, 2, n, Qblk[i], ldQ[i], m, QZ, ldQZ, c, S2, ldS, QZ, ldQZ, S3, ldS, flags, 1, true));
+            if (backend != CALZ_QR_TSQR)
+                CALZ_TRY(chol_small(ctx, c, S3 + m, R2, flags + 2, nullptr, 0, nullptr, flags, 1, backend == CALZ_QR_CHOLQR2,
+                                    backend == CALZ_QR_CHOLQR2 ? flags + 4 : nullptr, ldS));
+            else   // one Householder TSQR of whatever QZ holds now (Z, or Y if pass 2 did not fire): the LAST normalize
+                CALZ_TRY(tsqr_factor(ctx, n, c, QZ, ldQZ, R1, nullptr, 0));
+        }
         src = QZ;
         ldsrc = ldQZ;
     } else {
@@ -335,7 +344,9 @@ static int pan_enqueue(calz_ctx* ctx, int64_t n, int nblk, const double* const* 
         }
     }
     // ---- Q of the LAST normalize only
-    if (backend != CALZ_QR_TSQR) {
+    if (fused_solve) {
+        // done above
+    } else if (backend != CALZ_QR_TSQR) {
         CALZ_TRY(select_r(ctx, c, R1, R2, flags, flags + 3, flags + 4, Rf, flags + 5));
         CALZ_TRY(ts_trsolve(ctx, n, c, src, ldsrc, Rf, QZ, ldQZ, nullptr, 0));
     } else {

@@ -10,6 +10,9 @@
 //   pass 1  COEFF   S1 = [Q X]'X               -> C1 = Q'X (project.m:34) and diag(X'X) = ||x_i||^2 (pAN.m:17-22)
 //   pass 2  UPDATE  Y = X - Q*C1 (project.m:35), S2 = [Q Y]'Y -> C2 = Q'Y (2nd pass, pAN.m:63) and G_Y = Y'Y (cholqr.m:5)
 //   pass 3  UPDATE  Z = Y - Q*C2 in place,      S3 = Z'Z       (cholqr.m:5 of the second normalize, pAN.m:64)
+//   pass 3' SOLVE   QZ = ((X - Q*C1) - Q*C2) / R, nothing contracted (R from the downdated Gram, k_chol_pan): replaces
+//                   pass 3 AND the separate triangular solve for the Cholesky back ends.  Y = X - Q*C1 is RE-computed in
+//                   registers (bit-identical to pass 2), so pass 2 does not have to write Y to HBM at all.
 // Reductions are deterministic: fixed warp order inside the CTA, per-CTA partials, last CTA sums them in a fixed order.
 #include <algorithm>
 
@@ -24,7 +27,7 @@ constexpr int kPitch = 132;                     // doubles per column slot: 132 
 constexpr int kConsumerWarps = 8;
 constexpr int kTileThreads = (kConsumerWarps + 1) * 32;
 
-enum { MODE_COEFF = 0, MODE_UPDATE_FULL = 1, MODE_UPDATE_GRAM = 2 };
+enum { MODE_COEFF = 0, MODE_UPDATE_FULL = 1, MODE_UPDATE_GRAM = 2, MODE_UPDATE_SOLVE = 3 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -61,6 +64,8 @@ struct TileArgs {
     const double* X; long long ldX; int c;          // block being orthogonalised (input of this pass)
     double* Y; long long ldY;                       // update modes: where the updated block goes (may alias X)
     const double* C; int ldC;                       // update modes: coefficients (M x c, device)
+    const double* R;                                // solve mode: c x c upper triangular factor (device, dense)
+    const double* C2; int ldC2; const int* flag2;   // solve mode: second coefficient block, applied iff *flag2 != 0
     double* S; int ldS;                             // result: rows [0,M) = Q-part, rows [M, M+c) = block-part  (x c columns)
     double* partials; unsigned int* ticket;
     const int* pred; int want;
@@ -72,7 +77,8 @@ __global__ void __launch_bounds__(kTileThreads, 1)
 k_tile(TileArgs p, int stages) {
     if (p.pred && *p.pred != p.want) return;
     constexpr int SLOTS = 8 * (MT + CT);
-    constexpr bool ACC_Q = (MODE != MODE_UPDATE_GRAM);           // accumulate the Q-row tiles too
+    constexpr bool SOLVE = (MODE == MODE_UPDATE_SOLVE);
+    constexpr bool ACC_Q = (MODE != MODE_UPDATE_GRAM) && !SOLVE;  // accumulate the Q-row tiles too
     constexpr int RT0 = ACC_Q ? 0 : MT;                           // first row-tile that is accumulated
     constexpr int NRT = MT + CT - RT0;
     constexpr int CW = 8 * CT;
@@ -80,8 +86,9 @@ k_tile(TileArgs p, int stages) {
     double* tiles = reinterpret_cast<double*>(smem_raw);
     const size_t stage_doubles = (size_t)SLOTS * kPitch;
     double* Cs = tiles + (size_t)stages * stage_doubles;          // [MT*8][CW]
-    double* red = Cs + (size_t)MT * 8 * CW;                       // [kConsumerWarps][NRT*CT*64]
-    uint64_t* full = reinterpret_cast<uint64_t*>(red + (size_t)kConsumerWarps * NRT * CT * 64);
+    double* red = Cs + (size_t)MT * 8 * CW;                       // [kConsumerWarps][NRT*CT*64]   (solve mode: Rs[CW][CW+1], Cs2)
+    double* Cs2 = red + (size_t)CW * (CW + 1);                    // solve mode only: [MT*8][CW]
+    uint64_t* full = reinterpret_cast<uint64_t*>(red + (SOLVE ? (size_t)CW * (CW + 1) + (size_t)MT * 8 * CW + CW : (size_t)kConsumerWarps * NRT * CT * 64));
     uint64_t* empty = full + stages;
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -102,6 +109,18 @@ k_tile(TileArgs p, int stages) {
             const int m = e / CW, j = e % CW;
             Cs[e] = (m < p.M && j < p.c) ? p.C[(size_t)j * p.ldC + m] : 0.0;
         }
+    const bool second = SOLVE && p.flag2 && *p.flag2 != 0;
+    if (SOLVE) {
+        for (int e = tid; e < CW * CW; e += kTileThreads) {
+            const int i = e / CW, j = e % CW;
+            red[i * (CW + 1) + j] = (i < p.c && j < p.c) ? p.R[(size_t)j * p.c + i] : (i == j ? 1.0 : 0.0);
+        }
+        for (int e = tid; e < MT * 8 * CW; e += kTileThreads) {
+            const int m = e / CW, j = e % CW;
+            Cs2[e] = (second && m < p.M && j < p.c) ? p.C2[(size_t)j * p.ldC2 + m] : 0.0;
+        }
+        for (int j = tid; j < CW; j += kTileThreads) Cs2[(size_t)MT * 8 * CW + j] = j < p.c ? 1.0 / p.R[(size_t)j * p.c + j] : 1.0;
+    }
     __syncthreads();
 
     if (warp == kConsumerWarps) {
@@ -159,24 +178,80 @@ k_tile(TileArgs p, int stages) {
                 double y[HC];
 #pragma unroll
                 for (int j = 0; j < HC; ++j) y[j] = T[(size_t)(8 * MT + half * HC + j) * kPitch + row];
-#pragma unroll 3
-                for (int m = 0; m < p.M; ++m) {
-                    const double q = T[(size_t)m * kPitch + row];
+                if (SOLVE && second) {
+                    // Y = X - Q*C1 and, sharing the loads of Q, t = Q*C2; then Z = Y - t (project.m:35 of the second pass:
+                    // the product is formed first and subtracted once, like the reference's GEMM + subtraction)
+                    double t[HC];
 #pragma unroll
-                    for (int j = 0; j < HC; ++j) y[j] = fma(-q, Cs[m * CW + half * HC + j], y[j]);
+                    for (int j = 0; j < HC; ++j) t[j] = 0.0;
+#pragma unroll 3
+                    for (int m = 0; m < p.M; ++m) {
+                        const double q = T[(size_t)m * kPitch + row];
+#pragma unroll
+                        for (int j = 0; j < HC; ++j) {
+                            y[j] = fma(-q, Cs[m * CW + half * HC + j], y[j]);
+                            t[j] = fma(q, Cs2[m * CW + half * HC + j], t[j]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < HC; ++j) y[j] -= t[j];
+                } else {
+#pragma unroll 3
+                    for (int m = 0; m < p.M; ++m) {
+                        const double q = T[(size_t)m * kPitch + row];
+#pragma unroll
+                        for (int j = 0; j < HC; ++j) y[j] = fma(-q, Cs[m * CW + half * HC + j], y[j]);
+                    }
                 }
                 const bool ok = r0 + row < p.n;
+                if (SOLVE) {
+                    // ---- forward substitution along the row, q_j = (z_j - sum_{i<j} q_i R_ij) / R_jj, same operation order
+                    //      as k_trsolve; the thread of the upper column half picks q_0..q_{HC-1} up from shared memory
+                    const double* Rs = red;
+                    const double* Rinv = Cs2 + (size_t)MT * 8 * CW;      // 1/R_jj, rounded once (as in k_trsolve)
+                    if (half == 0) {
 #pragma unroll
-                for (int j = 0; j < HC; ++j) {
-                    const int col = half * HC + j;
-                    T[(size_t)(8 * MT + col) * kPitch + row] = y[j];
-                    if (ok && col < p.c) p.Y[(long long)col * p.ldY + r0 + row] = y[j];
+                        for (int j = 0; j < HC; ++j) {
+                            double sacc = y[j];
+#pragma unroll
+                            for (int i = 0; i < j; ++i) sacc = fma(-y[i], Rs[i * (CW + 1) + j], sacc);
+                            y[j] = sacc * Rinv[j];
+                            T[(size_t)(8 * MT + j) * kPitch + row] = y[j];
+                        }
+                    }
+                    consumer_sync();
+                    if (half == 1) {
+                        double ql[HC];
+#pragma unroll
+                        for (int i = 0; i < HC; ++i) ql[i] = T[(size_t)(8 * MT + i) * kPitch + row];
+#pragma unroll
+                        for (int j = 0; j < HC; ++j) {
+                            double sacc = y[j];
+#pragma unroll
+                            for (int i = 0; i < HC; ++i) sacc = fma(-ql[i], Rs[i * (CW + 1) + HC + j], sacc);
+#pragma unroll
+                            for (int i = 0; i < j; ++i) sacc = fma(-y[i], Rs[(HC + i) * (CW + 1) + HC + j], sacc);
+                            y[j] = sacc * Rinv[HC + j];
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < HC; ++j) {
+                        const int col = half * HC + j;
+                        if (ok && col < p.c) p.Y[(long long)col * p.ldY + r0 + row] = y[j];
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < HC; ++j) {
+                        const int col = half * HC + j;
+                        T[(size_t)(8 * MT + col) * kPitch + row] = y[j];
+                        if (p.Y && ok && col < p.c) p.Y[(long long)col * p.ldY + r0 + row] = y[j];
+                    }
+                    consumer_sync();                 // the whole Y tile is in shared memory before anyone contracts it
                 }
-                consumer_sync();                 // the whole Y tile is in shared memory before anyone contracts it
             }
             // ---- contraction over the 16 rows of this warp: S += [Q Y]' Y
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < (SOLVE ? 0 : 4); ++u) {
                 const int row = 16 * warp + 4 * u + tq;
                 double bf[CT], af[NRT];
 #pragma unroll
@@ -198,7 +273,7 @@ k_tile(TileArgs p, int stages) {
         // ---- CTA reduction over the consumer warps (fixed order)
         double* mine = red + (size_t)warp * NRT * CT * 64;
 #pragma unroll
-        for (int a = 0; a < NRT; ++a)
+        for (int a = 0; a < (SOLVE ? 0 : NRT); ++a)
 #pragma unroll
             for (int b = 0; b < CT; ++b) {
                 double* tile = mine + (a * CT + b) * 64;
@@ -206,6 +281,7 @@ k_tile(TileArgs p, int stages) {
                 tile[g * 8 + 2 * tq + 1] = acc[a][b][1];
             }
     }
+    if (SOLVE) return;
     __syncthreads();
     constexpr int ELEMS = NRT * CT * 64;
     double* out = p.partials + (size_t)blockIdx.x * ELEMS;
@@ -259,9 +335,11 @@ template <int MT, int CT, int MODE>
 int launch_tile(calz_ctx* ctx, const TileArgs& a0) {
     TileArgs a = a0;
     constexpr int SLOTS = 8 * (MT + CT);
-    constexpr int NRT = (MODE == MODE_UPDATE_GRAM) ? CT : MT + CT;
+    constexpr bool SOLVE = (MODE == MODE_UPDATE_SOLVE);
+    constexpr int NRT = (MODE == MODE_UPDATE_GRAM || SOLVE) ? CT : MT + CT;
     const size_t stage_bytes = (size_t)SLOTS * kPitch * sizeof(double);
-    const size_t fixed = ((size_t)MT * 8 * 8 * CT + (size_t)kConsumerWarps * NRT * CT * 64) * sizeof(double) + 2 * 8 * sizeof(uint64_t) + 64;
+    const size_t red_doubles = SOLVE ? (size_t)(8 * CT) * (8 * CT + 1) + (size_t)MT * 8 * 8 * CT + 8 * CT : (size_t)kConsumerWarps * NRT * CT * 64;
+    const size_t fixed = ((size_t)MT * 8 * 8 * CT + red_doubles) * sizeof(double) + 2 * 8 * sizeof(uint64_t) + 64;
     int dev_max = 0;
     cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device);
     // aim for 2 CTAs per SM: 228 KB per SM minus 1 KB the driver reserves per resident CTA
@@ -279,11 +357,14 @@ int launch_tile(calz_ctx* ctx, const TileArgs& a0) {
     per_sm = std::min(per_sm, 2);
     const long long ntiles = (a.n + kTileRows - 1) / kTileRows;
     const int grid = (int)std::max<long long>(1, std::min<long long>((long long)ctx->num_sms * per_sm, ntiles));
-    CALZ_TRY(reserve(ctx, ctx->partials, (size_t)grid * NRT * CT * 64 * sizeof(double)));
-    a.partials = (double*)ctx->partials.p;
+    if (!SOLVE) {
+        CALZ_TRY(reserve(ctx, ctx->partials, (size_t)grid * NRT * CT * 64 * sizeof(double)));
+        a.partials = (double*)ctx->partials.p;
+    }
     a.ticket = ctx->ticket;
     kern<<<grid, kTileThreads, smem, ctx->stream>>>(a, stages);
     CALZ_LAUNCH_CHECK(ctx);
+    if (SOLVE) return CALZ_OK;
     k_tile_finalize<MT, CT, MODE><<<(NRT * CT * 64 + 7) / 8, 256, 0, ctx->stream>>>(a.partials, grid, a.S, a.ldS, a.M, a.c, a.pred, a.want);
     CALZ_LAUNCH_CHECK(ctx);
     return CALZ_OK;
@@ -324,6 +405,21 @@ int tile_pass(calz_ctx* ctx, int mode, int64_t n, const double* Q, int64_t ldQ, 
         CALZ_TRY(allreduce_sum(ctx, S_dev, (size_t)ldS * c));
     }
     return CALZ_OK;
+}
+
+// QZ = ((X - Q*C1) - [*flag2] Q*C2) / R in ONE pass over [Q | X].  Same per-row arithmetic as the UPDATE passes followed by
+// k_trsolve.
+int tile_update_solve(calz_ctx* ctx, int64_t n, const double* Q, int64_t ldQ, int M, const double* X, int64_t ldX, int c,
+                      const double* C1_dev, int ldC1, const double* C2_dev, int ldC2, const int* flag2, const double* R_dev, double* QZ,
+                      int64_t ldQZ) {
+    TileArgs a{};
+    a.n = n; a.Q = Q; a.ldQ = ldQ; a.M = M; a.X = X; a.ldX = ldX; a.c = c; a.Y = QZ; a.ldY = ldQZ; a.C = C1_dev; a.ldC = ldC1;
+    a.C2 = C2_dev; a.ldC2 = ldC2; a.flag2 = flag2; a.R = R_dev;
+    const int MT = (M + 7) / 8, CT = (c + 7) / 8;
+    if (MT == 1 && CT == 1) return launch_tile<1, 1, MODE_UPDATE_SOLVE>(ctx, a);
+    if (MT == 2 && CT == 1) return launch_tile<2, 1, MODE_UPDATE_SOLVE>(ctx, a);
+    if (MT == 1 && CT == 2) return launch_tile<1, 2, MODE_UPDATE_SOLVE>(ctx, a);
+    return launch_tile<2, 2, MODE_UPDATE_SOLVE>(ctx, a);
 }
 
 }  // namespace calz

@@ -253,7 +253,7 @@ int ts_update(calz_ctx* ctx, int64_t n, const double* Q, int64_t ldQ, int M, con
 }
 
 // ------------------------------------------------------------------------------------------ X / R
-// One row per thread, forward substitution along the row: q_j = (x_j - sum_{i<j} q_i R_ij) / R_jj.
+// One row per thread, forward substitution along the row: q_j = (x_j - sum_{i<j} q_i R_ij) * (1/R_jj).
 template <int CT>
 __global__ void __launch_bounds__(kTsThreads, (CT == 1 ? 4 : (CT == 2 ? 3 : 2)))
 k_trsolve(long long n, int c, const double* X, long long ldX, const double* __restrict__ R, double* Q, long long ldQ,
@@ -261,10 +261,12 @@ k_trsolve(long long n, int c, const double* X, long long ldX, const double* __re
     if (pred && *pred != want) return;
     constexpr int CW = 8 * CT;
     __shared__ double Rs[CW][CW + 1];
+    __shared__ double Rinv[CW];                       // 1/R_jj rounded once; q_j = s * (1/R_jj) (2 roundings instead of a 30-instruction divide)
     for (int e = threadIdx.x; e < CW * CW; e += kTsThreads) {
         const int i = e / CW, j = e % CW;
         Rs[i][j] = (i < c && j < c) ? R[(size_t)j * c + i] : (i == j ? 1.0 : 0.0);
     }
+    for (int j = threadIdx.x; j < CW; j += kTsThreads) Rinv[j] = j < c ? 1.0 / R[(size_t)j * c + j] : 1.0;
     __syncthreads();
     // one row per thread, no grid-stride loop: keeps R in shared memory instead of 36..528 hoisted registers
     const long long r = (long long)blockIdx.x * kTsThreads + threadIdx.x;
@@ -278,7 +280,7 @@ k_trsolve(long long n, int c, const double* X, long long ldX, const double* __re
                 double s = q[j];
 #pragma unroll
                 for (int i = 0; i < j; ++i) s = fma(-q[i], Rs[i][j], s);
-                q[j] = s / Rs[j][j];
+                q[j] = s * Rinv[j];
             }
         }
 #pragma unroll
@@ -318,21 +320,25 @@ __device__ void norm_drop_flag(int c, const double (*R)[kMaxC + 1], const double
 }
 
 // One warp.  adaptive != 0 (CALZ_QR_CHOLQR2): a failed pivot restarts the factorisation of G + shift*I (shifted CholQR,
-// shift = 100*c*eps*max(diag G), x100 per retry) instead of giving up; *info_out = -(#shifts) then.  cond_out (optional):
-// 1 if a shift was needed or min_j R_jj/sqrt(G_jj) < thresh, i.e. one CholQR pass is not Householder-accurate.
-__global__ void k_chol_small(int c, const double* __restrict__ G, double* __restrict__ Rout, int* info_out,
-                             const double* __restrict__ nb2, int nb2_stride, int* flag_out,
-                             const int* __restrict__ pred, int want, int adaptive, double thresh, int* cond_out, int ldG) {
-    if (pred && *pred != want) return;
-    __shared__ double A[kMaxC][kMaxC + 1];
-    const int lane = threadIdx.x;
-    double gdiag = (lane < c) ? G[(size_t)lane * ldG + lane] : 0.0, gmax = gdiag;
+// shift = 100*c*eps*max(diag G), x100 per retry) instead of giving up; nshift counts the retries.
+// Cd (optional, Md x c, leading dimension ldCd): factor the DOWNDATED matrix G - Cd'Cd instead (see k_chol_pan).
+// Returns info (0 or the failing pivot); A holds R in its upper triangle; gdiag_out = this lane's diagonal entry of the
+// matrix that was factored.
+__device__ int chol_warp(int c, double (*A)[kMaxC + 1], const double* __restrict__ G, int ldG, const double* __restrict__ Cd,
+                         int ldCd, int Md, int adaptive, int lane, double* gdiag_out, int* nshift_out) {
+    auto entry = [&](int i, int j) {
+        double v = G[(size_t)j * ldG + i];
+        if (Cd)
+            for (int m = 0; m < Md; ++m) v = fma(-Cd[(size_t)i * ldCd + m], Cd[(size_t)j * ldCd + m], v);
+        return v;
+    };
+    double gdiag = (lane < c) ? entry(lane, lane) : 0.0, gmax = gdiag;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) gmax = fmax(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
     double shift = 0.0;
     int info = 0, nshift = 0;
     while (true) {
-        for (int e = lane; e < c * c; e += 32) A[e % c][e / c] = G[(size_t)(e / c) * ldG + e % c] + ((e % c == e / c) ? shift : 0.0);     // A[i][j] = G(i,j)
+        for (int e = lane; e < c * c; e += 32) A[e % c][e / c] = entry(e % c, e / c) + ((e % c == e / c) ? shift : 0.0);     // A[i][j] = G(i,j)
         __syncwarp();
         info = 0;
         // right-looking upper Cholesky, lane l owns column l
@@ -354,6 +360,28 @@ __global__ void k_chol_small(int c, const double* __restrict__ G, double* __rest
         shift = (nshift == 1) ? 100.0 * c * 2.220446049250313e-16 * gmax : shift * 100.0;
         __syncwarp();
     }
+    *gdiag_out = gdiag;
+    *nshift_out = nshift;
+    return info;
+}
+
+// 1 if a shift was needed or min_j R_jj/sqrt(G_jj) < thresh, i.e. one CholQR pass is not Householder-accurate
+__device__ int chol_cond_flag(int c, const double (*A)[kMaxC + 1], double gdiag, int info, int nshift, double thresh, int lane) {
+    double worst = (lane < c) ? (gdiag > 0.0 ? A[lane][lane] / sqrt(gdiag) : 0.0) : 1.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) worst = fmin(worst, __shfl_xor_sync(0xffffffffu, worst, o));
+    return (info == 0 && (nshift > 0 || worst < thresh)) ? 1 : 0;
+}
+
+__global__ void k_chol_small(int c, const double* __restrict__ G, double* __restrict__ Rout, int* info_out,
+                             const double* __restrict__ nb2, int nb2_stride, int* flag_out,
+                             const int* __restrict__ pred, int want, int adaptive, double thresh, int* cond_out, int ldG) {
+    if (pred && *pred != want) return;
+    __shared__ double A[kMaxC][kMaxC + 1];
+    const int lane = threadIdx.x;
+    double gdiag;
+    int nshift;
+    const int info = chol_warp(c, A, G, ldG, nullptr, 0, 0, adaptive, lane, &gdiag, &nshift);
     for (int e = lane; e < c * c; e += 32) {
         const int i = e % c, j = e / c;
         Rout[e] = (i <= j) ? A[i][j] : 0.0;
@@ -361,15 +389,70 @@ __global__ void k_chol_small(int c, const double* __restrict__ G, double* __rest
     if (lane == 0 && info_out) *info_out = info ? info : -nshift;
     __syncwarp();
     if (cond_out) {
-        double worst = (lane < c) ? (gdiag > 0.0 ? A[lane][lane] / sqrt(gdiag) : 0.0) : 1.0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) worst = fmin(worst, __shfl_xor_sync(0xffffffffu, worst, o));
-        if (lane == 0) *cond_out = (info == 0 && (nshift > 0 || worst < thresh)) ? 1 : 0;
+        const int cf = chol_cond_flag(c, A, gdiag, info, nshift, thresh, lane);
+        if (lane == 0) *cond_out = cf;
     }
     if (flag_out) {
         if (info != 0) { if (lane == 0) *flag_out = 0; }
         else norm_drop_flag(c, A, nb2, nb2_stride, flag_out, lane);
     }
+}
+
+// The whole small-matrix step of the fused projectAndNormalize pipeline in ONE launch (one warp).  S2 = [C2; G_Y] comes from
+// tile pass 2 (C2 = Q'Y is M x c, G_Y = Y'Y is c x c, leading dimension ldS):
+//   R1 = chol(G_Y), the 50 % norm-drop test (projectAndNormalize.m:45-52) -> flags[0];
+//   if it fires: R2 = chol(G_Y - C2'C2).  Z = Y - Q*C2 with Q'Q = I gives Z'Z = G_Y - C2'C2 exactly, and C2 is the
+//   O(eps*||x||) left-over of the first projection, so the downdate loses nothing against forming Z'Z from Z (the
+//   correction is far below the rounding of G_Y itself) -- and the pass over HBM that would form Z'Z is not needed:
+//   Z is only ever produced inside the final fused update + triangular-solve pass.
+//   Rf = the R of the last normalize, flags[5] = its conditioning flag (CholQR2).
+// flags: [0] second pass, [1]/[2] chol info pass 1/2, [3]/[4] conditioning flag pass 1/2, [5] selected
+__global__ void k_chol_pan(int c, int M, const double* __restrict__ S2, int ldS, const double* __restrict__ nb2, int nb2_stride,
+                           int adaptive, double thresh, double* __restrict__ R1, double* __restrict__ R2, double* __restrict__ Rf,
+                           int* __restrict__ flags) {
+    __shared__ double A[kMaxC][kMaxC + 1];
+    __shared__ int s_second;
+    const int lane = threadIdx.x;
+    const double* G = S2 + M;
+    double gdiag;
+    int nshift;
+    int info = chol_warp(c, A, G, ldS, nullptr, 0, 0, adaptive, lane, &gdiag, &nshift);
+    for (int e = lane; e < c * c; e += 32) {
+        const int i = e % c, j = e / c;
+        const double r = (i <= j) ? A[i][j] : 0.0;
+        R1[e] = r;
+        Rf[e] = r;
+    }
+    __syncwarp();
+    int cond = adaptive ? chol_cond_flag(c, A, gdiag, info, nshift, thresh, lane) : 0;
+    if (info != 0) { if (lane == 0) s_second = 0; }
+    else norm_drop_flag(c, A, nb2, nb2_stride, &s_second, lane);
+    __syncwarp();
+    const int second = s_second;
+    if (lane == 0) { flags[0] = second; flags[1] = info ? info : -nshift; flags[3] = cond; }
+    if (second) {
+        __syncwarp();
+        info = chol_warp(c, A, G, ldS, S2, ldS, M, adaptive, lane, &gdiag, &nshift);
+        for (int e = lane; e < c * c; e += 32) {
+            const int i = e % c, j = e / c;
+            const double r = (i <= j) ? A[i][j] : 0.0;
+            R2[e] = r;
+            Rf[e] = r;
+        }
+        __syncwarp();
+        cond = adaptive ? chol_cond_flag(c, A, gdiag, info, nshift, thresh, lane) : 0;
+        if (lane == 0) { flags[2] = info ? info : -nshift; flags[4] = cond; }
+    }
+    if (lane == 0) flags[5] = cond;
+}
+
+int chol_pan(calz_ctx* ctx, int c, int M, const double* S2, int ldS, const double* nb2, int nb2_stride, bool adaptive, double* R1,
+             double* R2, double* Rf, int* flags) {
+    if (c > kMaxC) return set_error(ctx, CALZ_ERR_UNSUPPORTED, "block width c=%d > %d", c, kMaxC);
+    k_chol_pan<<<1, 32, 0, ctx->stream>>>(c, M, S2, ldS, nb2, nb2_stride, adaptive ? 1 : 0, 1.0 / (double)ctx->opt_cholqr2_inv_thresh,
+                                          R1, R2, Rf, flags);
+    CALZ_LAUNCH_CHECK(ctx);
+    return CALZ_OK;
 }
 
 int chol_small(calz_ctx* ctx, int c, const double* G_dev, double* R_dev, int* info_out, const double* nb2,

@@ -50,6 +50,14 @@ int chol_small(calz_ctx* ctx, int c, const double* G_dev, double* R_dev, int* in
                int nb2_stride, int* flag_out, const int* pred, int want, bool adaptive = false, int* cond_out = nullptr,
                int ldG = 0);
 
+// fused small-matrix step of the tile pipeline: R1 = chol(G_Y), norm-drop test, R2 = chol(G_Y - C2'C2) if it fires, Rf, flags
+int chol_pan(calz_ctx* ctx, int c, int M, const double* S2, int ldS, const double* nb2, int nb2_stride, bool adaptive, double* R1,
+             double* R2, double* Rf, int* flags);
+// final fused pass: QZ = ((X - Q*C1) - [*flag2] Q*C2) / R in one sweep over [Q | X] (tiles.cu)
+int tile_update_solve(calz_ctx* ctx, int64_t n, const double* Q, int64_t ldQ, int M, const double* X, int64_t ldX, int c,
+                      const double* C1_dev, int ldC1, const double* C2_dev, int ldC2, const int* flag2, const double* R_dev, double* QZ,
+                      int64_t ldQZ);
+
 // fused TMA-tile passes of projectAndNormalize (tiles.cu)
 bool tile_path_ok(int64_t n, const double* Q, int64_t ldQ, int M, const double* X, int64_t ldX, int c, const double* Y, int64_t ldY);
 int tile_pass(calz_ctx* ctx, int mode, int64_t n, const double* Q, int64_t ldQ, int M, const double* X, int64_t ldX, int c,

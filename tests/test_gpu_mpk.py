@@ -95,6 +95,49 @@ def test_dictionary_coded_sell_is_bit_identical(name):
     assert relcols(outs["selld"][0], kernels.matrix_powers_newton(A, v, 5, lam, 1)) < TOL
 
 
+def _few_values_ragged(n=5000, seed=3):
+    # few distinct (offset, value) pairs but a different sparsity pattern in every row: the codes of a warp diverge
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    offs = np.array([-40, -7, -1, 0, 1, 7, 40, 300])
+    vals = np.array([-1.0, 0.5, -2.0, 6.0, -2.0, 0.5, -1.0, 0.25])
+    rows, cols, data = [], [], []
+    for r in range(n):
+        for k in np.flatnonzero(rng.random(offs.size) < 0.6):
+            c = r + offs[k]
+            if 0 <= c < n:
+                rows.append(r); cols.append(c); data.append(vals[k])
+    return sp.csr_matrix((data, (rows, cols)), shape=(n, n))
+
+
+@pytest.mark.parametrize("name", ["lap3d", "ragged"])
+def test_dictionary_kernel_variants_are_bit_identical(name):
+    # the dictionary lives in the constant bank (warp-uniform codes) or in shared memory (ragged codes); persistent
+    # software-pipelined grid or one work item per warp: four kernels, one answer
+    A = MATS["lap3d"]() if name == "lap3d" else _few_values_ragged()
+    n = A.shape[0]
+    v = np.cos(0.11 * np.arange(n)) + 0.3
+    lam = np.array([5.0, 0.5, 3.0, 1.0])
+    ctx = api.default_context()
+    ref_dm = api.DeviceMatrix(A, 4, "sell")
+    ref = (api.matrix_powers_newton(ref_dm, v, 4, lam, 1), api.matrix_powers_monomial(ref_dm, v, 3))
+    ref_dm.close()
+    dm = api.DeviceMatrix(A, 4, "selld")
+    uni = dm.info("dict_uniform_pct")
+    assert 0 <= uni <= 100 and (name == "lap3d" or uni < 50)     # short grid lines: partly uniform; ragged: not at all
+    try:
+        for dmode in (-1, 0, 2):
+            for persist in (1, 0):
+                ctx.set_option("mpk_dict_mode", dmode)
+                ctx.set_option("mpk_persist", persist)
+                np.testing.assert_array_equal(api.matrix_powers_newton(dm, v, 4, lam, 1), ref[0])
+                np.testing.assert_array_equal(api.matrix_powers_monomial(dm, v, 3), ref[1])
+    finally:
+        ctx.set_option("mpk_dict_mode", -1)
+        ctx.set_option("mpk_persist", 1)
+        dm.close()
+
+
 @pytest.mark.parametrize("name", ["poisson100", "lap3d"])
 def test_tma_staged_dictionary_kernel_is_bit_identical(name):
     # opt-in variant: the x segments of a CTA's row block are bulk-copied into shared memory (cp.async.bulk + mbarrier)

@@ -181,6 +181,38 @@ def test_project_and_normalize(backend, n, ms, c):
             assert np.linalg.norm(q.T @ QZ) < 1e-11
 
 
+@pytest.mark.parametrize("backend", ["cholqr", "cholqr2"])
+@pytest.mark.parametrize("n,m,c", [(50000, 9, 8), (33000, 16, 16), (4099, 5, 3)])
+def test_fused_last_pass_matches_three_pass_pipeline(backend, n, m, c):
+    # default: R2 = chol(G_Y - C2'C2) and ONE fused pass QZ = (Y - Q*C2)/R2; pan_fused_solve=0: Z written, Z'Z formed from Z,
+    # separate triangular solve.  Same mathematics; the downdate may differ from the explicit Gram by rounding only.
+    ctx = api.default_context()
+    Qp = _orthobasis(n, m, 5)
+    far = gallery.tall_skinny(n, c, seed=9)
+    near = Qp @ np.ones((m, c)) + 1e-2 * gallery.tall_skinny(n, c, seed=10)
+    for X, second in ((far, False), (near, True)):
+        out = {}
+        for fused in (1, 0):
+            ctx.set_option("pan_fused_solve", fused)
+            try:
+                info = {}
+                QZ, RZ = api.projectAndNormalize([Qp], X, True, backend=backend, info=info)
+            finally:
+                ctx.set_option("pan_fused_solve", 1)
+            assert info["second_pass"] == second
+            out[fused] = (QZ, RZ)
+        (Q1, R1), (Q0, R0) = out[1], out[0]
+        if not second:
+            np.testing.assert_array_equal(Q1, Q0)
+            np.testing.assert_array_equal(R1[-1], R0[-1])
+        kappa = np.linalg.cond(R0[-1])
+        assert rel(R1[0], R0[0]) < 1e-14
+        assert rel(R1[-1], R0[-1]) < 50 * kappa * EPS
+        assert rel(Q1, Q0) < 50 * kappa * EPS
+        assert orth(Q1) <= max(10 * orth(Q0), 1e-13)
+        assert np.linalg.norm(Qp.T @ Q1) < 1e-11
+
+
 def test_pan_without_reorth():
     n = 3000
     Q = [_orthobasis(n, 5, 1)]
