@@ -364,6 +364,7 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
         int32_t wmax = 0;
         for (int64_t l = 0; l < n_loc; ++l) wmax = std::max(wmax, rowlen[l]);
         if (wmax > 64) dict_ok = false;                       // very long rows: the byte stream per lane gets too ragged
+        if (n_loc >= ((int64_t)1 << 28) - 64) dict_ok = false;   // byte offsets and row indices are 32-bit in the kernel
     }
     if (layout == CALZ_LAYOUT_SELL_DICT && !dict_ok) {
         delete m;
@@ -379,7 +380,7 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
 
     if (layout == CALZ_LAYOUT_SELL_DICT) {
         // per slice of 32 rows: ceil(width/8) blocks of 32 lanes x 8 code bytes (one coalesced 256-B load per block)
-        std::vector<int32_t> slice_ptr(m->sell_slices + 1, 0);
+        std::vector<int32_t> slice_ptr(m->sell_slices + 2, 0);                  // + one padding entry (the kernel reads [s .. s+2])
         int64_t blocks = 0;
         for (int64_t sl = 0; sl < m->sell_slices; ++sl) {
             int32_t w = 0;
@@ -388,6 +389,7 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
             blocks += (w + 7) / 8;
         }
         slice_ptr[m->sell_slices] = (int32_t)blocks;
+        slice_ptr[m->sell_slices + 1] = (int32_t)blocks;
         std::vector<uint8_t> packed((size_t)blocks * 256, (uint8_t)255);        // 255 = padding code
         for (int64_t sl = 0; sl < m->sell_slices; ++sl)
             for (int64_t r = sl * C; r < std::min<int64_t>(n_loc, sl * C + C); ++r)
@@ -413,8 +415,8 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
             dict[2 * k] = dict_val[k];
             long long o = dict_off[k];
             memcpy(&dict[2 * k + 1], &o, 8);
-            m->h_dict->v[k] = dict_val[k];
-            m->h_dict->offb[k] = (int)(o * 8);
+            m->h_dict->e[k].v = dict_val[k];
+            m->h_dict->e[k].offb = (int)(o * 8);
         }
         m->sell_padded = blocks * 256;
         m->dict_size = (int)dict_val.size();

@@ -46,7 +46,8 @@ struct calz_mat {
     double* d_dict = nullptr;
     int dict_size = 0;
     double dict_uniform = 0.0;                        // fraction of (block, slot) positions whose 32 lanes share one code
-    struct { double v[256]; int offb[256]; } h_dict[1] = {};   // host copy, passed to the kernels as a constant-bank parameter
+    struct alignas(16) HostDictEnt { double v; int offb; int pad; };
+    struct { HostDictEnt e[256]; } h_dict[1] = {};       // host copy, passed to the kernels as a constant-bank parameter
     // ... and its TMA-staged kernel: x segments of a CTA's row block (merged over overlapping offsets)
     int xs_rows = 0;                                  // rows per CTA (0: staged kernel not applicable)
     int xs_groups = 0;

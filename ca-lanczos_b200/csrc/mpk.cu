@@ -66,9 +66,13 @@ k_spmv_sell(const int32_t* __restrict__ slice_ptr, const int32_t* __restrict__ c
 constexpr int kDictSlicesPerWarp = 2;     // independent slices per warp: the loads of both are in flight together
 enum { DM_SHARED = 0, DM_CONST = 2 };
 
-struct DictParam {                        // 3 KB, passed by value as a __grid_constant__ kernel parameter
-    double v[256];
-    int offb[256];                        // column offset pre-scaled to bytes
+struct __align__(16) DictEnt {
+    double v;
+    int offb;                             // column offset pre-scaled to bytes
+    int pad;
+};
+struct DictParam {                        // 4 KB, passed by value as a __grid_constant__ kernel parameter
+    DictEnt e[256];
 };
 
 template <int DM>
@@ -80,8 +84,8 @@ __device__ __forceinline__ uint32_t dict_stage(unsigned char* sraw, const DictPa
         asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"(t));
     }
     for (int i = threadIdx.x; i < 256; i += kSpmvThreads) {
-        *reinterpret_cast<double*>(sraw + 8 * i) = P.v[i];
-        *reinterpret_cast<int*>(sraw + 2048 + 4 * i) = P.offb[i];
+        *reinterpret_cast<double*>(sraw + 8 * i) = P.e[i].v;
+        *reinterpret_cast<int*>(sraw + 2048 + 4 * i) = P.e[i].offb;
     }
     __syncthreads();
     return sbase;
@@ -97,13 +101,16 @@ __device__ __forceinline__ void dict_fma8(const DictParam& P, uint32_t sbase, co
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             const unsigned int half = q < 4 ? w[i].x : w[i].y;
-            const unsigned int c = (half >> (8 * (q & 3))) & 0xffu;
-            if (c != 255u) {
+            // the code byte already scaled to the 16-byte entry stride: (c << 4) in one shift + one mask
+            const unsigned int c16 = ((q & 3) == 0 ? (half << 4) : (half >> (8 * (q & 3) - 4))) & 0xff0u;
+            const unsigned int c = c16 >> 4;
+            if (c16 != 0xff0u) {
                 double v;
                 int ob;
                 if (DM == DM_CONST) {
-                    v = P.v[c];
-                    ob = P.offb[c];
+                    const DictEnt& e = *reinterpret_cast<const DictEnt*>(reinterpret_cast<const char*>(P.e) + c16);
+                    v = e.v;
+                    ob = e.offb;
                 } else {
                     asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"((c << 3) | sbase));
                     asm volatile("ld.shared.s32 %0, [%1+2048];" : "=r"(ob) : "r"((c << 2) | sbase));
@@ -114,71 +121,73 @@ __device__ __forceinline__ void dict_fma8(const DictParam& P, uint32_t sbase, co
     }
 }
 
-// PERSIST: an occupancy-sized grid, every warp strides over work items of NS slices, and the dependent chain
+// PERSIST: an occupancy-sized grid, every warp strides over work items of NS = 2 adjacent slices, and the dependent chain
 // slice_ptr -> codes -> x is software pipelined (the slice pointers of item i+2 and the code words of item i+1 are in flight
-// while the x gathers of item i are issued).  !PERSIST: one work item per warp.
+// while the x gathers of item i are issued).  !PERSIST: one work item per warp.  All indices are 32-bit (n_loc < 2^31 - 64;
+// slice_ptr carries one padding entry so that slice_ptr[s+2] is always readable).
 template <bool NEWTON, bool PERSIST, int DM>
 __global__ void __launch_bounds__(kSpmvThreads, 5)
 k_spmv_selld(const int32_t* __restrict__ slice_ptr, const uint2* __restrict__ codes, const __grid_constant__ DictParam P,
-             const double* __restrict__ x, const double* __restrict__ xprev, double* __restrict__ y, int64_t slice_lo,
-             int64_t slice_hi, int64_t n_loc, double shift, double pair) {
+             const double* __restrict__ x, const double* __restrict__ xprev, double* __restrict__ y, int slice_lo,
+             int slice_hi, int n_loc, double shift, double pair) {
     constexpr int NS = kDictSlicesPerWarp;
+    static_assert(NS == 2, "the pointer loads below fetch slice_ptr[s .. s+2]");
     __shared__ __align__(4096) unsigned char sraw[DM == DM_CONST ? 16 : 4096];
     const int lane = threadIdx.x & 31;
-    const int64_t items = (slice_hi - slice_lo + NS - 1) / NS;
-    const int64_t stride = PERSIST ? (int64_t)gridDim.x * (kSpmvThreads / 32) : items;
-    int64_t it = (int64_t)blockIdx.x * (kSpmvThreads / 32) + (threadIdx.x >> 5);
+    const int items = (slice_hi - slice_lo + NS - 1) / NS;
+    const int stride = PERSIST ? (int)gridDim.x * (kSpmvThreads / 32) : items;
+    int it = (int)blockIdx.x * (kSpmvThreads / 32) + (threadIdx.x >> 5);
+    const uint2* __restrict__ cl = codes + lane;
+
+    auto load_ptrs = [&](int item, int32_t (&p)[NS], int32_t (&n)[NS]) {
+        p[0] = p[1] = 0;
+        n[0] = n[1] = 0;
+        if (item < items) {
+            const int s = slice_lo + item * NS;
+            const int32_t a = __ldg(slice_ptr + s), b = __ldg(slice_ptr + s + 1), c = __ldg(slice_ptr + s + 2);
+            p[0] = a;
+            n[0] = b - a;
+            p[1] = b;
+            n[1] = (s + 1 < slice_hi) ? c - b : 0;
+        }
+    };
+    auto load_codes = [&](const int32_t (&p)[NS], const int32_t (&n)[NS], int b, uint2 (&w)[NS]) {
+#pragma unroll
+        for (int i = 0; i < NS; ++i) w[i] = (b < n[i]) ? __ldg(cl + ((size_t)(p[i] + b) << 5)) : make_uint2(~0u, ~0u);
+    };
+
     // prologue: pointers of items it and it+stride, code words of item it
     int32_t p0[NS], nb[NS], p0n[NS], nbn[NS];
     uint2 w[NS];
-#pragma unroll
-    for (int i = 0; i < NS; ++i) {
-        const int64_t sa = slice_lo + it * NS + i, sb = slice_lo + (it + stride) * NS + i;
-        const bool oka = it < items && sa < slice_hi, okb = PERSIST && it + stride < items && sb < slice_hi;
-        p0[i] = oka ? __ldg(slice_ptr + sa) : 0;
-        nb[i] = oka ? __ldg(slice_ptr + sa + 1) - p0[i] : 0;
-        p0n[i] = okb ? __ldg(slice_ptr + sb) : 0;
-        nbn[i] = okb ? __ldg(slice_ptr + sb + 1) - p0n[i] : 0;
-    }
-#pragma unroll
-    for (int i = 0; i < NS; ++i) w[i] = nb[i] > 0 ? __ldg(codes + (int64_t)p0[i] * 32 + lane) : make_uint2(~0u, ~0u);
+    load_ptrs(it, p0, nb);
+    if (PERSIST) load_ptrs(it + stride, p0n, nbn);
+    load_codes(p0, nb, 0, w);
     const uint32_t sbase = dict_stage<DM>(sraw, P);
     for (; it < items; it += stride) {
         uint2 wn[NS];
         int32_t p0nn[NS], nbnn[NS];
         if (PERSIST) {   // prefetch: code words of the next item, slice pointers of the one after
-#pragma unroll
-            for (int i = 0; i < NS; ++i) wn[i] = nbn[i] > 0 ? __ldg(codes + (int64_t)p0n[i] * 32 + lane) : make_uint2(~0u, ~0u);
-#pragma unroll
-            for (int i = 0; i < NS; ++i) {
-                const int64_t sc = slice_lo + (it + 2 * stride) * NS + i;
-                const bool okc = it + 2 * stride < items && sc < slice_hi;
-                p0nn[i] = okc ? __ldg(slice_ptr + sc) : 0;
-                nbnn[i] = okc ? __ldg(slice_ptr + sc + 1) - p0nn[i] : 0;
-            }
+            load_codes(p0n, nbn, 0, wn);
+            load_ptrs(it + 2 * stride, p0nn, nbnn);
         }
-        const int64_t slice0 = slice_lo + it * NS;
+        const int row0 = (slice_lo + it * NS) * 32 + lane;
         double sum[NS];
         const char* xr[NS];
-        int maxb = 0;
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             sum[i] = 0.0;
-            xr[i] = reinterpret_cast<const char*>(x + min((slice0 + i) * 32 + lane, n_loc - 1));
-            maxb = max(maxb, nb[i]);
+            xr[i] = reinterpret_cast<const char*>(x + (row0 + 32 * i));
         }
-        for (int b = 0; b < maxb; ++b) {
-            if (b > 0) {
-#pragma unroll
-                for (int i = 0; i < NS; ++i)
-                    w[i] = (b < nb[i]) ? __ldg(codes + (int64_t)(p0[i] + b) * 32 + lane) : make_uint2(~0u, ~0u);
-            }
+        dict_fma8<DM, NS>(P, sbase, w, xr, sum);
+        const int maxb = max(nb[0], nb[1]);
+        for (int b = 1; b < maxb; ++b) {          // rows with more than 8 non-zeros
+            load_codes(p0, nb, b, w);
             dict_fma8<DM, NS>(P, sbase, w, xr, sum);
         }
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
-            const int64_t r = (slice0 + i) * 32 + lane;
-            if (slice0 + i < slice_hi && r < n_loc) {
+            const int r = row0 + 32 * i;
+            if (r < n_loc && (i == 0 || slice_lo + it * NS + i < slice_hi)) {
                 double v = sum[i];
                 if (NEWTON) v = newton_epilogue(v, x[r], pair != 0.0 ? xprev[r] : 0.0, shift, pair);
                 y[r] = v;
@@ -346,6 +355,7 @@ int launch_csr(calz_mat* m, const double* x, const double* xp, double* y, int64_
 
 template <bool NEWTON, bool PERSIST, int DM>
 int launch_selld_t(calz_mat* m, const double* x, const double* xp, double* y, int64_t s0, int64_t s1, double shift, double pair) {
+    if (s1 <= s0) return CALZ_OK;
     calz_ctx* ctx = m->ctx;
     const int64_t per_cta = (int64_t)(kSpmvThreads / 32) * kDictSlicesPerWarp;
     unsigned grid = (unsigned)((s1 - s0 + per_cta - 1) / per_cta);
@@ -359,7 +369,7 @@ int launch_selld_t(calz_mat* m, const double* x, const double* xp, double* y, in
         if (grid > cap) grid = cap;
     }
     k_spmv_selld<NEWTON, PERSIST, DM><<<grid, kSpmvThreads, 0, ctx->stream>>>(m->d_slice_ptr, (const uint2*)m->d_codes, *(const DictParam*)m->h_dict,
-                                                                             x, xp, y, s0, s1, m->n_loc, shift, pair);
+                                                                             x, xp, y, (int)s0, (int)s1, (int)m->n_loc, shift, pair);
     CALZ_LAUNCH_CHECK(ctx);
     return CALZ_OK;
 }
