@@ -3,7 +3,7 @@
 // One persistent CTA per resident slot streams 128-row tiles of the tall-skinny operands [Q | X] through a
 // multi-stage shared-memory ring: a producer warp issues one 1-D TMA bulk copy (cp.async.bulk, mbarrier
 // complete_tx) per column, 8 consumer warps
-//   - (update modes) apply  Y = X - Q*C  one row per thread pair straight in shared memory and stream Y back to HBM,
+//   - (update modes) apply  Y = X - Q*C  with fp64 DMMA on the 16 rows the warp owns, in shared memory, and stream Y back to HBM,
 //   - contract the tile over its rows with fp64 DMMA (mma.sync m8n8k4), fragments read conflict-free from
 //     shared memory (column pitch 132 doubles),
 // so every operand crosses HBM exactly once per pass:
@@ -53,7 +53,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerWarps * 32) : "memory"); }
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
@@ -164,6 +163,15 @@ k_tile(TileArgs p, int stages) {
         for (int a = 0; a < NRT; ++a)
 #pragma unroll
             for (int b = 0; b < CT; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+        // A fragments of the update GEMMs: -C1' (and -C2' for the solve pass), constant over the tiles
+        double a1[2 * MT][CT], a2[2 * MT][CT];
+#pragma unroll
+        for (int ks = 0; ks < 2 * MT; ++ks)
+#pragma unroll
+            for (int b = 0; b < CT; ++b) {
+                a1[ks][b] = (MODE != MODE_COEFF) ? -Cs[(4 * ks + tq) * CW + 8 * b + g] : 0.0;
+                a2[ks][b] = SOLVE ? -Cs2[(4 * ks + tq) * CW + 8 * b + g] : 0.0;
+            }
         int it = 0;
         for (long long t = blockIdx.x; t < ntiles; t += gridDim.x, ++it) {
             const int s = it % stages;
@@ -172,43 +180,54 @@ k_tile(TileArgs p, int stages) {
             double* T = tiles + (size_t)s * stage_doubles;
             const long long r0 = t * kTileRows;
             if (MODE != MODE_COEFF) {
-                // ---- Y = X - Q*C : thread (row, half) owns CW/2 columns of one row
-                constexpr int HC = CW / 2;
-                const int row = tid & (kTileRows - 1), half = tid >> 7;
-                double y[HC];
+                // ---- Y = X - Q*C on the tensor pipe, warp-local: the warp updates the SAME 16 rows it contracts below, so no
+                //      CTA-wide barrier is needed.  Per 8-row group: D(8 cols x 8 rows) = X' + (-C')(8 x K) * Q'(K x 8 rows);
+                //      thread (g, tq) holds D[col g][rows 2tq, 2tq+1], A[col g][k tq] = -C(k, col), B[k tq][row g] = Q(row, k).
 #pragma unroll
-                for (int j = 0; j < HC; ++j) y[j] = T[(size_t)(8 * MT + half * HC + j) * kPitch + row];
-                if (SOLVE && second) {
-                    // Y = X - Q*C1 and, sharing the loads of Q, t = Q*C2; then Z = Y - t (project.m:35 of the second pass:
-                    // the product is formed first and subtracted once, like the reference's GEMM + subtraction)
-                    double t[HC];
+                for (int h = 0; h < 2; ++h) {
+                    const int rbase = 16 * warp + 8 * h;
+                    double d[CT][2], bq[2 * MT];
 #pragma unroll
-                    for (int j = 0; j < HC; ++j) t[j] = 0.0;
-#pragma unroll 3
-                    for (int m = 0; m < p.M; ++m) {
-                        const double q = T[(size_t)m * kPitch + row];
+                    for (int b = 0; b < CT; ++b) {
+                        const double2 xv = *reinterpret_cast<const double2*>(&T[(size_t)(8 * MT + 8 * b + g) * kPitch + rbase + 2 * tq]);
+                        d[b][0] = xv.x;
+                        d[b][1] = xv.y;
+                    }
 #pragma unroll
-                        for (int j = 0; j < HC; ++j) {
-                            y[j] = fma(-q, Cs[m * CW + half * HC + j], y[j]);
-                            t[j] = fma(q, Cs2[m * CW + half * HC + j], t[j]);
+                    for (int ks = 0; ks < 2 * MT; ++ks) bq[ks] = T[(size_t)(4 * ks + tq) * kPitch + rbase + g];
+#pragma unroll
+                    for (int ks = 0; ks < 2 * MT; ++ks)
+#pragma unroll
+                        for (int b = 0; b < CT; ++b) dmma(d[b][0], d[b][1], a1[ks][b], bq[ks]);
+                    if (SOLVE && second) {       // Z = Y - Q*C2: the reference's second projection pass (project.m:35)
+#pragma unroll
+                        for (int ks = 0; ks < 2 * MT; ++ks)
+#pragma unroll
+                            for (int b = 0; b < CT; ++b) dmma(d[b][0], d[b][1], a2[ks][b], bq[ks]);
+                    }
+#pragma unroll
+                    for (int b = 0; b < CT; ++b) {
+                        *reinterpret_cast<double2*>(&T[(size_t)(8 * MT + 8 * b + g) * kPitch + rbase + 2 * tq]) = make_double2(d[b][0], d[b][1]);
+                        if (!SOLVE && p.Y && 8 * b + g < p.c) {
+                            const long long r = r0 + rbase + 2 * tq;
+                            double* dst = p.Y + (long long)(8 * b + g) * p.ldY + r;
+                            if (r + 1 < p.n) *reinterpret_cast<double2*>(dst) = make_double2(d[b][0], d[b][1]);
+                            else if (r < p.n) *dst = d[b][0];
                         }
                     }
-#pragma unroll
-                    for (int j = 0; j < HC; ++j) y[j] -= t[j];
-                } else {
-#pragma unroll 3
-                    for (int m = 0; m < p.M; ++m) {
-                        const double q = T[(size_t)m * kPitch + row];
-#pragma unroll
-                        for (int j = 0; j < HC; ++j) y[j] = fma(-q, Cs[m * CW + half * HC + j], y[j]);
-                    }
                 }
-                const bool ok = r0 + row < p.n;
+                __syncwarp();                    // the warp's 16 rows of Y are in shared memory
                 if (SOLVE) {
-                    // ---- forward substitution along the row, q_j = (z_j - sum_{i<j} q_i R_ij) / R_jj, same operation order
-                    //      as k_trsolve; the thread of the upper column half picks q_0..q_{HC-1} up from shared memory
+                    // ---- forward substitution along the row, q_j = (z_j - sum_{i<j} q_i R_ij) * (1/R_jj), same operation order as
+                    //      k_trsolve.  Lane (row = lane & 15, half = lane >> 4) owns CW/2 columns of one of the warp's 16 rows; the
+                    //      lane of the upper column half picks q_0..q_{HC-1} up from shared memory.
+                    constexpr int HC = CW / 2;
+                    const int row = 16 * warp + (lane & 15), half = lane >> 4;
                     const double* Rs = red;
                     const double* Rinv = Cs2 + (size_t)MT * 8 * CW;      // 1/R_jj, rounded once (as in k_trsolve)
+                    double y[HC];
+#pragma unroll
+                    for (int j = 0; j < HC; ++j) y[j] = T[(size_t)(8 * MT + half * HC + j) * kPitch + row];
                     if (half == 0) {
 #pragma unroll
                         for (int j = 0; j < HC; ++j) {
@@ -219,7 +238,7 @@ k_tile(TileArgs p, int stages) {
                             T[(size_t)(8 * MT + j) * kPitch + row] = y[j];
                         }
                     }
-                    consumer_sync();
+                    __syncwarp();
                     if (half == 1) {
                         double ql[HC];
 #pragma unroll
@@ -234,19 +253,12 @@ k_tile(TileArgs p, int stages) {
                             y[j] = sacc * Rinv[HC + j];
                         }
                     }
+                    const bool ok = r0 + row < p.n;
 #pragma unroll
                     for (int j = 0; j < HC; ++j) {
                         const int col = half * HC + j;
                         if (ok && col < p.c) p.Y[(long long)col * p.ldY + r0 + row] = y[j];
                     }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < HC; ++j) {
-                        const int col = half * HC + j;
-                        T[(size_t)(8 * MT + col) * kPitch + row] = y[j];
-                        if (p.Y && ok && col < p.c) p.Y[(long long)col * p.ldY + r0 + row] = y[j];
-                    }
-                    consumer_sync();                 // the whole Y tile is in shared memory before anyone contracts it
                 }
             }
             // ---- contraction over the 16 rows of this warp: S += [Q Y]' Y
