@@ -334,7 +334,7 @@ def run_b200(args):
     }
     if e2e is not None:
         line["e2e"] = e2e
-    if not args.no_cpu and world >= 1:
+    if not args.no_cpu and world == 1:      # reported baseline: rank 0 at N=1 only
         div = 8 if m >= 64 else 1
         mz = max(m // div, 2 * s + 2)
         dt, nrows = cpu_block_seconds(m, mz, s, shifts, args.backend)

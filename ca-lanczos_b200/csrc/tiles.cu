@@ -98,10 +98,13 @@ k_tile(TileArgs p, int stages) {
         for (int s = 0; s < stages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
         fence_barrier_init();
     }
-    for (size_t e = tid; e < (size_t)stages * stage_doubles; e += kTileThreads) {
-        const int slot = (int)((e % stage_doubles) / kPitch);
-        const bool used = (slot < 8 * MT) ? (slot < p.M) : (slot - 8 * MT < p.c);
-        if (!used) tiles[e] = 0.0;
+    {   // only the padding slots (columns M..8MT-1 and c..8CT-1 of every stage) are ever read without being written by TMA
+        const int padQ = 8 * MT - p.M, npad = padQ + 8 * CT - p.c;
+        for (int e = tid; e < stages * npad * kTileRows; e += kTileThreads) {
+            const int r = e % kTileRows, k = (e / kTileRows) % npad, st = e / (kTileRows * npad);
+            const int slot = k < padQ ? p.M + k : 8 * MT + p.c + (k - padQ);
+            tiles[(size_t)st * stage_doubles + (size_t)slot * kPitch + r] = 0.0;
+        }
     }
     if (MODE != MODE_COEFF)
         for (int e = tid; e < MT * 8 * CW; e += kTileThreads) {
