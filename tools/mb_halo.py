@@ -12,7 +12,7 @@ m, s = int(sys.argv[1]) if len(sys.argv) > 1 else 256, 8
 n, plane = m ** 3, m * m
 lo, hi = (rank * n) // world, ((rank + 1) * n) // world
 hl, hh = max(0, lo - s * plane), min(n, hi + s * plane)
-dm = api.DeviceMatrix(gallery.laplace3d(m, row_lo=hl, row_hi=hh), s_max=s, layout="sell", ctx=ctx, n_glob=n, row_begin=hl)
+dm = api.DeviceMatrix(gallery.laplace3d(m, row_lo=hl, row_hi=hh), s_max=s, layout=os.environ.get("MB_LAYOUT", "auto"), ctx=ctx, n_glob=n, row_begin=hl)
 stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 v = torch.full((dm.n,), 1.0 / np.sqrt(n), dtype=torch.float64, device=dev); torch.cuda.synchronize()
 re = np.ascontiguousarray(gallery.leja_points(0, 12, s))
