@@ -171,8 +171,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "ca_lanczos_s_step_blocks_per_sec", "value": value, "unit": "blocks/s",
             "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 / value,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(m, s, args.backend), "n": m ** 3, "s": s, "basis": "newton",
-                       "orth": "cholqr" if args.backend != "tsqr" else "tsqr"},
+            "config": {"workload": workload_name(m, s, args.backend), "n": m ** 3, "nnz": 7 * m ** 3 - 6 * m * m, "s": s, "basis": "newton",
+                       "orth": args.backend, "layout": "scipy-csr", "partition": "host"},
             "cpu_baseline": {"value": value, "unit": "blocks/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "blocks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0,
