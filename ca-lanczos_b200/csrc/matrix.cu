@@ -92,7 +92,7 @@ int calz_mat_destroy(calz_mat* m) {
     if (m->ctx) cudaStreamSynchronize(m->ctx->stream);
     p2p_halo_teardown(m);
     void* ptrs[] = {m->d_xs_off, m->d_codes, m->d_dict, m->d_send_idx, m->d_send_buf, m->d_rowptr, m->d_colind, m->d_val, m->d_slice_ptr,
-                    m->d_sell_col, m->d_sell_val, m->d_perm, m->d_W};
+                    m->d_sell_col, m->d_sell_val, m->d_perm, m->d_W_alloc};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete m;
@@ -504,13 +504,17 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
 
     // ---- basis workspace
     m->ldW = round_up(n_loc, 32);
-    size_t wbytes = (size_t)m->ldW * (size_t)(s_max + 1) * sizeof(double);
-    cudaError_t e = cudaMalloc(&m->d_W, wbytes);
+    // The OWNED rows of every column must start 16-byte aligned on every rank (TMA bulk copies; and every rank has to take the
+    // same orthogonalisation path, or the collectives no longer match): shift the workspace by one double when own_off is odd.
+    m->W_pad = (int)(m->own_off & 1);
+    size_t wbytes = ((size_t)m->ldW * (size_t)(s_max + 1) + 2) * sizeof(double);
+    cudaError_t e = cudaMalloc(&m->d_W_alloc, wbytes);
     if (e != cudaSuccess) {
         calz_mat_destroy(m);
         return set_error(ctx, CALZ_ERR_ALLOC, "basis workspace %zu bytes: %s", wbytes, cudaGetErrorString(e));
     }
-    CALZ_CUDA(ctx, cudaMemset(m->d_W, 0, wbytes));
+    CALZ_CUDA(ctx, cudaMemset(m->d_W_alloc, 0, wbytes));
+    m->d_W = m->d_W_alloc + m->W_pad;
     if (P > 1) CALZ_TRY(p2p_halo_setup(m));
     *out = m;
     return CALZ_OK;

@@ -25,6 +25,7 @@ struct calz_mat {
     // peer-memory halo (p2p.cu): the peers' basis workspaces and where my rows land in them
     bool p2p_halo = false;
     std::vector<double*> peer_W;
+    std::vector<void*> peer_W_base;                  // what cudaIpcOpenMemHandle returned (to close it)
     std::vector<long long> peer_dst_off;
 
     // CSR (local indices)
@@ -56,7 +57,9 @@ struct calz_mat {
     int* d_xs_off = nullptr;                          // per code: position of x[row+offset] relative to (row - r0)
 
     // basis workspace n_loc x (s_max+1), ghosts included
-    double* d_W = nullptr;
+    double* d_W = nullptr;                            // d_W_alloc + W_pad: (d_W + own_off) is 16-byte aligned
+    double* d_W_alloc = nullptr;
+    int W_pad = 0;
     int64_t ldW = 0;
 };
 

@@ -397,7 +397,7 @@ int spmv_step(calz_mat* m, const double* x, const double* xp, double* y, int64_t
               double shift, double pair) {
     if (hi <= lo) return CALZ_OK;
     calz_ctx* ctx = m->ctx;
-    if (m->layout == CALZ_LAYOUT_SELL_DICT && m->xs_rows > 0 && ctx->opt_mpk_tma_x) {
+    if (m->layout == CALZ_LAYOUT_SELL_DICT && m->xs_rows > 0 && ctx->opt_mpk_tma_x && m->W_pad == 0) {   // bulk copies need 16-B aligned x segments
         const int64_t s0 = lo / 32, s1 = (hi + 31) / 32;
         const int spc = m->xs_rows / 32;
         const unsigned grid = (unsigned)((s1 - s0 + spc - 1) / spc);

@@ -122,7 +122,7 @@ __global__ void k_halo_ack(HaloWait hw, int me, unsigned long long seq) {
     if (threadIdx.x < hw.n) st_release_sys(hw.peer_flags[threadIdx.x] + kFlagHaloAck + me, seq);
 }
 
-// exchange `bytes` (<= 120) per rank with every peer through NCCL send/recv (bit-exact: no arithmetic)
+// exchange `bytes` per rank with every peer through NCCL send/recv (bit-exact: no arithmetic)
 int exchange_blobs(calz_ctx* ctx, const void* mine, size_t bytes, std::vector<std::vector<unsigned char>>& all) {
     const int P = ctx->nranks;
     const size_t nd = (bytes + 7) / 8;
@@ -248,9 +248,10 @@ int p2p_halo_setup(calz_mat* m) {
     m->p2p_halo = false;
     if (!ctx->p2p.enabled) return CALZ_OK;
     const int P = ctx->nranks;
-    struct Blob { cudaIpcMemHandle_t h; long long recv_off[kMaxPeers]; int ok; } blob;
+    struct Blob { cudaIpcMemHandle_t h; long long recv_off[kMaxPeers]; int ok; int w_pad; } blob;
     memset(&blob, 0, sizeof(blob));
-    cudaError_t e = cudaIpcGetMemHandle(&blob.h, m->d_W);
+    cudaError_t e = cudaIpcGetMemHandle(&blob.h, m->d_W_alloc);
+    blob.w_pad = m->W_pad;
     blob.ok = (e == cudaSuccess);
     if (!blob.ok) cudaGetLastError();
     for (int q = 0; q < P; ++q) blob.recv_off[q] = m->recv_off[q];
@@ -259,13 +260,15 @@ int p2p_halo_setup(calz_mat* m) {
     bool all_ok = true;
     for (int q = 0; q < P; ++q) all_ok &= ((Blob*)all[q].data())->ok != 0;
     m->peer_W.assign(P, nullptr);
+    m->peer_W_base.assign(P, nullptr);
     m->peer_dst_off.assign(P, 0);
     for (int q = 0; q < P && all_ok; ++q) {
         if (q == ctx->rank || (m->send_cnt[q] == 0 && m->recv_cnt[q] == 0)) continue;
         void* ptr = nullptr;
         e = cudaIpcOpenMemHandle(&ptr, ((Blob*)all[q].data())->h, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) { cudaGetLastError(); all_ok = false; break; }
-        m->peer_W[q] = (double*)ptr;
+        m->peer_W[q] = (double*)ptr + ((Blob*)all[q].data())->w_pad;      // the peer's d_W (its allocation + alignment shift)
+        m->peer_W_base[q] = ptr;
         m->peer_dst_off[q] = ((Blob*)all[q].data())->recv_off[ctx->rank];      // where q receives MY rows
     }
     double verdict = all_ok ? 0.0 : 1.0, *d_v = nullptr;
@@ -282,9 +285,10 @@ int p2p_halo_setup(calz_mat* m) {
 }
 
 void p2p_halo_teardown(calz_mat* m) {
-    for (size_t q = 0; q < m->peer_W.size(); ++q)
-        if (m->peer_W[q]) cudaIpcCloseMemHandle(m->peer_W[q]);
+    for (size_t q = 0; q < m->peer_W_base.size(); ++q)
+        if (m->peer_W_base[q]) cudaIpcCloseMemHandle(m->peer_W_base[q]);
     m->peer_W.clear();
+    m->peer_W_base.clear();
 }
 
 // push my boundary rows of workspace column 0 into the peers' ghost zones, wait for theirs

@@ -25,9 +25,11 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--grid", type=int, default=40)
     ap.add_argument("--gridz", type=int, default=0)
-    ap.add_argument("--s", type=int, default=8)
+    ap.add_argument("--sstep", dest="s", type=int, default=8)       # not "--s": torchrun prefix-matches its own options
     ap.add_argument("--blocks", type=int, default=5)
     ap.add_argument("--backend", default="cholqr2")
+    ap.add_argument("--layout", default="auto")
+    ap.add_argument("--matrix", default="lap3d", choices=["lap3d", "powerlaw"])
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -40,12 +42,21 @@ def main():
 
     m, s = args.grid, args.s
     mz = args.gridz or m
-    n, plane = m * m * mz, m * m
-    lo, hi = (rank * n) // world, ((rank + 1) * n) // world
-    # supply exactly the level-(s) closure hull of a stencil: s planes either side (clipped)
-    have_lo, have_hi = max(0, lo - s * plane - plane), min(n, hi + s * plane + plane)
-    A_rows = gallery.laplace3d(m, m, mz, row_lo=have_lo, row_hi=have_hi)
-    dm = api.DeviceMatrix(A_rows, s_max=s, layout="sell", ctx=ctx, n_glob=n, row_begin=have_lo)
+    if args.matrix == "lap3d":
+        n, plane = m * m * mz, m * m
+        lo, hi = (rank * n) // world, ((rank + 1) * n) // world
+        # supply exactly the level-(s) closure hull of a stencil: s planes either side (clipped)
+        have_lo, have_hi = max(0, lo - s * plane - plane), min(n, hi + s * plane + plane)
+        A_rows = gallery.laplace3d(m, m, mz, row_lo=have_lo, row_hi=have_hi)
+        A = gallery.laplace3d(m, m, mz)
+    else:
+        # C4-like (scaled): power-law SPD, the level-s closure of a row block is (almost) every row, send lists are scattered
+        A = gallery.powerlaw_spd(20000, 8.0, seed=0)
+        n = A.shape[0]
+        lo, hi = (rank * n) // world, ((rank + 1) * n) // world
+        have_lo, have_hi = 0, n
+        A_rows = A
+    dm = api.DeviceMatrix(A_rows, s_max=s, layout=args.layout, ctx=ctx, n_glob=n, row_begin=have_lo)
     fails = []
 
     def check(name, ok, detail=""):
@@ -54,7 +65,6 @@ def main():
 
     # ---- integer objects: bit-exact against the oracle
     from oracle import partition
-    A = gallery.laplace3d(m, m, mz)
     b = partition.row_bounds(n, world)
     check("row bounds", (dm.info("row_lo"), dm.info("row_hi")) == (int(b[rank]), int(b[rank + 1])))
     ghosts = partition.ghost_indices(A, lo, hi, s)
@@ -67,10 +77,18 @@ def main():
     # ---- block pipeline vs the 1-way oracle driver
     from oracle import drivers, kernels
     r = np.cos(0.61 * np.arange(n) ** 1.5) + 0.3 * np.sin(1.7 * np.arange(n))
-    shifts = gallery.leja_points(0.0, 12.0, s)
-    Bk = np.zeros((s + 1, s)); Bk[np.arange(s), np.arange(s)] = shifts; Bk[np.arange(1, s + 1), np.arange(s)] = 1.0
     io = {}
-    To, Qo = drivers.ca_lanczos(A, r, s, s * args.blocks, "newton", "local", Bk=Bk, info=io)
+    if args.matrix == "lap3d":
+        shifts = gallery.leja_points(0.0, 12.0, s)
+        Bk = np.zeros((s + 1, s)); Bk[np.arange(s), np.arange(s)] = shifts; Bk[np.arange(1, s + 1), np.arange(s)] = 1.0
+        To, Qo = drivers.ca_lanczos(A, r, s, s * args.blocks, "newton", "local", Bk=Bk, info=io)
+        qtol = 1e-10
+    else:
+        # shifts from the oracle's own 2s-step Lanczos + Leja ordering (ca_lanczos.m:66-71); 'local' orthogonalisation keeps
+        # ||I-Q'Q|| ~ 1e-6 on this matrix, so two backward-stable QRs agree to ~1e-6 in Q (1 GPU: 5e-6) and ~1e-11 in T
+        To, Qo = drivers.ca_lanczos(A, r, s, s * args.blocks, "newton", "local", info=io)
+        shifts = np.diag(io["Bk"])[:s].copy()
+        qtol = 2e-5
     q0 = (r / np.sqrt(r @ r))[lo:hi]
     eng = BlockEngine(dm, s, args.blocks + 1, "newton", shifts, args.backend)
     eng.first_block(q0)
@@ -84,7 +102,7 @@ def main():
     ro = np.sort(np.linalg.eig(To)[0].real)[::-1]; rg = np.sort(np.linalg.eig(T)[0].real)[::-1]
     check("ritz 1e-8", np.max(np.abs(rg[:4] - ro[:4]) / np.abs(ro[:4])) < 1e-8)
     err = np.max(np.linalg.norm(Qloc - Qo[lo:hi, : Qloc.shape[1]], axis=0))
-    check("Q rows 1e-10", err < 1e-10, "%.3e" % err)
+    check("Q rows %.0e" % qtol, err < qtol, "%.3e" % err)
     # MPK alone, through the host flavour with the communicator (owned rows in, owned rows out)
     v = r / np.sqrt(r @ r)
     V = api.matrix_powers_newton(dm, v[lo:hi], s, shifts, 1)
@@ -101,7 +119,7 @@ def main():
     dist.all_gather_object(allf, fails)
     if rank == 0:
         flat = [f for fs in allf for f in fs]
-        print("dist_check P=%d m=%dx%dx%d s=%d backend=%s: %s" % (world, m, m, mz, s, args.backend, "OK" if not flat else "FAILED"))
+        print("dist_check P=%d %s n=%d s=%d backend=%s layout=%s: %s" % (world, args.matrix, n, s, args.backend, dm.layout, "OK" if not flat else "FAILED"))
         print("  max |T-To|/max|To| = %.2e, Q rows err %.2e, mpk err %.2e, ghosts %d" % (np.abs(T - To).max() / sc, err, e, ghosts.size))
         for f in flat:
             print("  " + f)

@@ -25,3 +25,15 @@ def test_two_rank_pipeline_matches_one_way_oracle(backend):
            "--master-port", "29541", os.path.join(ROOT, "tests", "dist_check.py"), "--grid", "32", "--backend", backend]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("backend", ["cholqr2", "tsqr"])
+def test_two_rank_scattered_exchange_powerlaw(backend):
+    # C4-like: dense level-s closure, scattered send lists (pack + push), very ragged rows
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29547", os.path.join(ROOT, "tests", "dist_check.py"), "--matrix", "powerlaw", "--sstep", "4", "--blocks", "4",
+           "--backend", backend]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
