@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--layout", default="auto", choices=["auto", "selld", "sell", "csr"])
     ap.add_argument("--l2-chunk-mb", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-gram", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-clocks", action="store_true")
     ap.add_argument("--sync-blocks", action="store_true", help="one host synchronisation per block (no pipelining)")
@@ -284,6 +285,31 @@ def run_b200(args):
     ritz_max = float(np.max(np.linalg.eigvals(eng.T_matrix()).real))
     second_frac = float(np.mean(eng.second)) if eng.second else 0.0
 
+    # ---- Gram X'X (the dense contraction of CholQR) against the fp64 tensor pipe, measured live (1 GPU only; not part of `value`)
+    gram = None
+    if world == 1 and not args.no_gram:
+        import ctypes as C
+        from ca_lanczos_b200 import _lib
+        tf = C.c_double()
+        _lib.check(ctx.lib.calz_dmma_peak(ctx.h, C.byref(tf)), ctx.h)
+        Cd = torch.zeros(s * s, dtype=torch.float64, device=dev)
+        xp = eng._qcol(1)
+        torch.cuda.synchronize(dev)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for rep in range(8):
+            if rep == 3:
+                g0.record(stream)
+            _lib.check(ctx.lib.calz_gram(ctx.h, n_own, s, xp, eng.ld, s, xp, eng.ld, Cd.data_ptr()), ctx.h)
+        g1.record(stream)
+        g1.synchronize()
+        gms = g0.elapsed_time(g1) / 5
+        gflop = 2.0 * n_own * s * s
+        gram = {"kernel": "k_tsmm_tn (Gram X'X of an n x %d block, mma.sync m8n8k4 f64)" % s, "bound": "tensor",
+                "achieved": gflop / (gms * 1e-3) / 1e12, "peak": tf.value, "unit": "TFLOP/s",
+                "frac": gflop / (gms * 1e-3) / 1e12 / tf.value, "peak_source": "measured live (calz_dmma_peak: register-resident DMMA chains)",
+                "launch_ms": gms, "hbm_frac": 8.0 * n_own * s / (gms * 1e-3) / 1e9 / measured_peak()[0],
+                "note": "intensity c/4 = %.2f flop/B keeps the Gram HBM-bound on B200 (SURVEY 8d): hbm_frac is the binding fraction" % (s / 4.0)}
+
     # ---- e2e: the same block through the reference-facing host API (host arrays in, host arrays out)
     e2e = None
     if not args.no_e2e:
@@ -334,6 +360,8 @@ def run_b200(args):
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if gram is not None:
+        line["roofline_gram"] = gram
     if not args.no_cpu and world == 1:      # reported baseline: rank 0 at N=1 only
         div = 8 if m >= 64 else 1
         mz = max(m // div, 2 * s + 2)
