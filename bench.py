@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--l2-chunk-mb", type=int, default=0)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-gram", action="store_true")
+    ap.add_argument("--no-sell-ref", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-clocks", action="store_true")
     ap.add_argument("--sync-blocks", action="store_true", help="one host synchronisation per block (no pipelining)")
@@ -310,6 +311,41 @@ def run_b200(args):
                 "launch_ms": gms, "hbm_frac": 8.0 * n_own * s / (gms * 1e-3) / 1e9 / measured_peak()[0],
                 "note": "intensity c/4 = %.2f flop/B keeps the Gram HBM-bound on B200 (SURVEY 8d): hbm_frac is the binding fraction" % (s / 4.0)}
 
+    # ---- the same MPK on the UNCOMPRESSED SELL layout (A really streamed from HBM): the conventional roofline number, measured live
+    sell_ref = None
+    if world == 1 and not args.no_sell_ref and dm.layout == "selld":
+        import ctypes as C
+        from ca_lanczos_b200 import _lib
+        dm2 = api.DeviceMatrix(gallery.laplace3d(m, m, mz), s_max=s, layout="sell", ctx=ctx)
+        re = np.ascontiguousarray(shifts, dtype=np.float64)
+        Vp, ldp = C.c_void_p(), C.c_int64()
+        qp = eng._qcol(1)
+
+        def mpk2():
+            _lib.check(ctx.lib.calz_mpk_inplace(dm2.h, C.c_void_p(qp), s, re.ctypes.data_as(_lib.c_dp), None, 1, 0, C.byref(Vp),
+                                                C.byref(ldp)), ctx.h)
+        for _ in range(3):
+            mpk2()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(5):
+            mpk2()
+        s1.record(stream)
+        s1.synchronize()
+        sms = s0.elapsed_time(s1) / (5 * s)
+        sbytes = 12 * nnz + 4 * (n + 1) + 16 * n
+        sell_traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                sell_traffic = json.load(f).get("k_spmv_sell_dram_bytes_per_launch")
+        except Exception:
+            pass
+        sell_ref = {"kernel": "k_spmv_sell (one SpMV step of the MPK, plain SELL-32: 12 B per non-zero streamed)", "bound": "hbm",
+                    "achieved": sbytes / (sms * 1e-3) / 1e9, "peak": measured_peak()[0], "unit": "GB/s",
+                    "frac": sbytes / (sms * 1e-3) / 1e9 / measured_peak()[0], "traffic": sell_traffic, "launch_ms": sms,
+                    "algorithmic_bytes_per_launch": sbytes}
+        dm2.close()
+
     # ---- e2e: the same block through the reference-facing host API (host arrays in, host arrays out)
     e2e = None
     if not args.no_e2e:
@@ -362,6 +398,8 @@ def run_b200(args):
         line["e2e"] = e2e
     if gram is not None:
         line["roofline_gram"] = gram
+    if sell_ref is not None:
+        line["roofline_sell"] = sell_ref
     if not args.no_cpu and world == 1:      # reported baseline: rank 0 at N=1 only
         div = 8 if m >= 64 else 1
         mz = max(m // div, 2 * s + 2)
