@@ -407,12 +407,22 @@ __global__ void k_chol_small(int c, const double* __restrict__ G, double* __rest
 //   Z is only ever produced inside the final fused update + triangular-solve pass.
 //   Rf = the R of the last normalize, flags[5] = its conditioning flag (CholQR2).
 // flags: [0] second pass, [1]/[2] chol info pass 1/2, [3]/[4] conditioning flag pass 1/2, [5] selected
-__global__ void k_chol_pan(int c, int M, const double* __restrict__ S2, int ldS, const double* __restrict__ nb2, int nb2_stride,
+constexpr int kCholPanStage = 1024;               // doubles: (M + c) * c <= 32 * 16 on the tile path
+
+__global__ void k_chol_pan(int c, int M, const double* S2, int ldS, const double* nb2, int nb2_stride,
                            int adaptive, double thresh, double* __restrict__ R1, double* __restrict__ R2, double* __restrict__ Rf,
                            int* __restrict__ flags) {
     __shared__ double A[kMaxC][kMaxC + 1];
+    __shared__ double sS[kCholPanStage];          // S2 and the squared norms staged once: everything below runs out of shared memory
+    __shared__ double snb[kMaxC];
     __shared__ int s_second;
     const int lane = threadIdx.x;
+    for (int e = lane; e < ldS * c; e += 32) sS[e] = S2[e];
+    if (lane < c) snb[lane] = nb2[(size_t)lane * nb2_stride];
+    __syncwarp();
+    S2 = sS;
+    nb2 = snb;
+    nb2_stride = 1;
     const double* G = S2 + M;
     double gdiag;
     int nshift;
@@ -448,7 +458,7 @@ __global__ void k_chol_pan(int c, int M, const double* __restrict__ S2, int ldS,
 
 int chol_pan(calz_ctx* ctx, int c, int M, const double* S2, int ldS, const double* nb2, int nb2_stride, bool adaptive, double* R1,
              double* R2, double* Rf, int* flags) {
-    if (c > kMaxC) return set_error(ctx, CALZ_ERR_UNSUPPORTED, "block width c=%d > %d", c, kMaxC);
+    if (c > kMaxC || ldS * c > kCholPanStage) return set_error(ctx, CALZ_ERR_UNSUPPORTED, "chol_pan: c=%d, ldS=%d too large", c, ldS);
     k_chol_pan<<<1, 32, 0, ctx->stream>>>(c, M, S2, ldS, nb2, nb2_stride, adaptive ? 1 : 0, 1.0 / (double)ctx->opt_cholqr2_inv_thresh,
                                           R1, R2, Rf, flags);
     CALZ_LAUNCH_CHECK(ctx);

@@ -19,7 +19,8 @@ namespace calz {
 
 namespace {
 
-constexpr int kTsqrThreads = 128;     // 4 warps per CTA, one leaf per warp at a time
+constexpr int kTsqrThreads = 64;      // 2 warps per CTA, one leaf per warp at a time: at ~180 registers per thread the
+                                      // register file holds 5 such CTAs (10 warps) per SM, but only 2 CTAs of 128 (8 warps)
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -217,7 +218,8 @@ std::map<calz_ctx*, Plan> g_plans;
 template <int CW, int RPL>
 int run_leaf(calz_ctx* ctx, const Level& L, int c, const double* A, long long ldA, const int* pred, int want) {
     const long long warps = (L.leaves + 0);
-    int grid = (int)std::min<long long>((warps + 3) / 4, (long long)ctx->num_sms * 8);
+    constexpr int WPC = kTsqrThreads / 32;
+    int grid = (int)std::min<long long>((warps + WPC - 1) / WPC, (long long)ctx->num_sms * 16);
     k_tsqr_leaf<CW, RPL><<<std::max(grid, 1), kTsqrThreads, 0, ctx->stream>>>(L.nrows, c, A, ldA, L.V, L.ldV, L.tau, L.Rstack, L.ldR, pred, want);
     CALZ_LAUNCH_CHECK(ctx);
     return CALZ_OK;
@@ -225,7 +227,8 @@ int run_leaf(calz_ctx* ctx, const Level& L, int c, const double* A, long long ld
 
 template <int CW, int RPL>
 int run_apply(calz_ctx* ctx, const Level& L, int c, const double* W, long long ldW, double* Out, long long ldOut) {
-    int grid = (int)std::min<long long>((L.leaves + 3) / 4, (long long)ctx->num_sms * 8);
+    constexpr int WPC = kTsqrThreads / 32;
+    int grid = (int)std::min<long long>((L.leaves + WPC - 1) / WPC, (long long)ctx->num_sms * 16);
     k_tsqr_apply<CW, RPL><<<std::max(grid, 1), kTsqrThreads, 0, ctx->stream>>>(L.nrows, c, L.V, L.ldV, L.tau, W, ldW, Out, ldOut);
     CALZ_LAUNCH_CHECK(ctx);
     return CALZ_OK;

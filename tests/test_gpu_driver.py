@@ -201,3 +201,58 @@ def test_ritz_vectors_and_residuals_on_device():
         assert vals[k] == pytest.approx(lam[i].real, rel=1e-14)
         assert res[k] == pytest.approx(ref, rel=1e-6, abs=1e-13)
     assert res[0] < 0.05 and 99.0 < vals[0] <= 100.0 + 1e-9                   # the top Ritz pair approaches lambda_max = 100
+
+
+def test_full_size_c3_block_properties():
+    # C3 at BASELINE size (256^3 7-point Laplacian, n = 16 777 216, s = 8 Newton, CholQR2, dictionary-coded SELL), device
+    # resident, checked through size-independent properties on the device:
+    #   the Lanczos relation  A Q(:,j) = Q(:,1:m+1) T(:,j)  (ca_lanczos.m:200-223 assembles T from the R factors only),
+    #   orthonormal blocks, adjacent blocks orthogonal, Ritz values inside the spectrum and approaching lambda_max.
+    import ctypes as C
+
+    import torch
+
+    from ca_lanczos_b200 import _lib
+    from ca_lanczos_b200.engine import BlockEngine
+
+    m, s, blocks = 256, 8, 4
+    A = gallery.laplace3d(m)
+    n = A.shape[0]
+    ctx = api.default_context()
+    dm = api.DeviceMatrix(A, s_max=s, ctx=ctx)
+    del A
+    assert dm.layout == "selld" and dm.info("dict_size") == 7
+    eng = BlockEngine(dm, s, blocks + 1, "newton", gallery.leja_points(0.0, 12.0, s), "cholqr2")
+    eng.first_block(np.full(n, 1.0 / np.sqrt(n)))
+    eng.run_blocks(blocks - 1)
+    assert eng.second == [True] * (blocks - 1)                    # the reference's second pass fires on every block here
+    ncol = s * blocks + 1
+    T = eng.T[:ncol, : ncol - 1]
+    dev = solver._Dev(dm)
+    buf = dev.zeros(3)
+    ax, rr, tmp = (dev.col(buf, j) for j in range(3))
+    relres = []
+    for j in (0, 5, 8, 15, 16, 23, 31):
+        dev.spmv(eng._qcol(j), ax)
+        cf = np.ascontiguousarray(T[:, j])
+        _lib.check(dev.lib.calz_block_axpy(ctx.h, n, ncol, C.c_void_p(eng._qcol(0)), eng.ld, 1, cf.ctypes.data_as(_lib.c_dp),
+                                           C.c_void_p(ax), dev.ld, C.c_void_p(rr), dev.ld), ctx.h)
+        relres.append(dev.normalize_col(rr, tmp) / 12.0)          # ||A q_j - Q T(:,j)|| against ||A|| ||q_j|| = 12
+    G = torch.zeros(s * (s + 1), dtype=torch.float64, device=buf.device)
+    orth_blk, orth_adj = [], []
+    for k in range(1, blocks):
+        qk, qp = eng._qcol(k * s + 1), eng._qcol((k - 1) * s + 1)
+        _lib.check(dev.lib.calz_gram(ctx.h, n, s, qk, eng.ld, s, qk, eng.ld, G.data_ptr()), ctx.h)
+        ctx.sync()
+        orth_blk.append(float(np.linalg.norm(G[: s * s].cpu().numpy().reshape(s, s) - np.eye(s))))
+        _lib.check(dev.lib.calz_gram(ctx.h, n, s, qp, eng.ld, s, qk, eng.ld, G.data_ptr()), ctx.h)
+        ctx.sync()
+        orth_adj.append(float(np.abs(G[: s * s].cpu().numpy()).max()))
+    ritz = np.linalg.eigvals(eng.T_matrix()).real
+    lam_max = 6.0 - 6.0 * np.cos(m * np.pi / (m + 1))
+    report = "relres %s orth_blk %s orth_adj %s ritz [%.6f, %.6f]" % (relres, orth_blk, orth_adj, ritz.min(), ritz.max())
+    assert max(relres) < 1e-9, report
+    assert max(orth_blk) < 1e-12 and max(orth_adj) < 1e-11, report
+    # 32 Lanczos steps from r = ones: the oracle reaches 11.854 on 64^3 (the extreme Ritz value barely depends on the grid)
+    assert ritz.min() > 0.0 and 11.8 < ritz.max() < lam_max + 1e-8, report
+    dm.close()
