@@ -94,14 +94,18 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
 
-    def mark(self):
+    def mark(self, wait_s=3.0):
+        """Call right before the timed region.  nvidia-smi needs a while to start: make sure it is already delivering samples."""
+        deadline = time.perf_counter() + wait_s
+        while self.proc and not self.rows and time.perf_counter() < deadline:
+            time.sleep(0.005)
         self.t0 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled"]}
         t1 = time.perf_counter()
-        time.sleep(0.05)
+        time.sleep(0.06)                          # let the samples taken inside the region reach the pipe
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         t0 = getattr(self, "t0", 0.0)
@@ -202,6 +206,7 @@ def run_b200(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+    sampler = ClockSampler(local, enabled=not args.no_clocks) if rank == 0 else None      # started early: nvidia-smi is slow to come up
     ctx = api.Context(local)
     if world > 1:
         ids = [api.Context.comm_unique_id() if rank == 0 else None]
@@ -240,12 +245,11 @@ def run_b200(args):
     # ---- timed region: exactly K blocks, CUDA events on libcalz' stream, per-phase events for the roofline
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     eng.phase_events = None
-    sampler = ClockSampler(local, enabled=not args.no_clocks) if rank == 0 else None
     if sampler:
-        time.sleep(0.3)                       # let nvidia-smi start before the timed region
+        sampler.mark()                        # waits (before the barrier) until nvidia-smi delivers samples
     barrier()
     if sampler:
-        sampler.mark()
+        sampler.mark(0.0)
     ctx.launch_count(reset=True)
     host_enqueue_ms = None
     e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
