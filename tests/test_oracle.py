@@ -203,3 +203,19 @@ def test_oracle_matches_committed_goldens(name):
         V = np.column_stack([q, kernels.matrix_powers_monomial(A, q, int(g["s"]))])
     rows = g["rows"]
     assert _relcols(V[rows], g["V_rows"]) < 1e-12
+
+
+def test_leja_shifts_agree_with_the_surveys_independent_restatement_up_to_the_tie():
+    # SURVEY.md 8c [scratch]: C2-template (N=500, linspace(1,100), s=8), first 8 Leja-ordered shifts from an INDEPENDENT restatement:
+    # 99.5677 1.4323 55.2117 19.8593 81.1407 36.5352 93.4271 7.5729.  The spectrum (and so the 16 Ritz values) is symmetric about
+    # 50.5, which makes the third Leja choice an exact tie between x and 101-x (|x-a||x-b| is symmetric); the winner depends on
+    # the last bit of pow() and every later choice mirrors it.  Both restatements must agree up to that mirror image.
+    A = gallery.diag_linspace(500, 100.0)
+    io = {}
+    drivers.ca_lanczos(A, np.ones(500), 8, 16, "newton", "local", info=io)
+    mine = np.diag(io["Bk"])[:8]
+    survey = np.array([99.5677, 1.4323, 55.2117, 19.8593, 81.1407, 36.5352, 93.4271, 7.5729])
+    np.testing.assert_allclose(mine[:2], survey[:2], atol=5e-5)
+    same = np.allclose(mine[2:], survey[2:], atol=5e-5)
+    mirrored = np.allclose(mine[2:], 101.0 - survey[2:], atol=5e-5)
+    assert same or mirrored
