@@ -256,3 +256,22 @@ def test_full_size_c3_block_properties():
     # 32 Lanczos steps from r = ones: the oracle reaches 11.854 on 64^3 (the extreme Ritz value barely depends on the grid)
     assert ritz.min() > 0.0 and 11.8 < ritz.max() < lam_max + 1e-8, report
     dm.close()
+
+
+@pytest.mark.skipif(os.environ.get("CALZ_TEST_EXPERIMENTAL", "0") != "1", reason="device adapter of the restarted driver not yet run on "
+                    "hardware (its control flow is covered on the CPU by tests/test_restart_host.py): CALZ_TEST_EXPERIMENTAL=1 enables it")
+@pytest.mark.parametrize("orth", ["local", "full"])
+def test_device_resident_restarted_ca_lanczos(orth):
+    # test_restart_diagonal_matrices.m:8-36 scaled down; Q, Q_conv and the restart vector never leave the GPU
+    from ca_lanczos_b200 import restart
+    N = 2000
+    A = gallery.diag_linspace(N, 1.0e2)
+    eo = drivers.restarted_ca_lanczos(A, np.ones(N), 40, 4, 4, "newton", orth, 1e-8)
+    eg = restart.device_restarted_ca_lanczos(A, np.ones(N), 40, 4, 4, "newton", orth, 1e-8, backend="tsqr")
+    exact = np.linspace(1, 100, N)[::-1][:4]
+    np.testing.assert_allclose(eg[0], exact, rtol=1e-8)
+    np.testing.assert_allclose(eg[0], eo[0], rtol=1e-8)
+    assert eg[2] == eo[2] and eg[3][-1].max() < 1e-8
+    Q = eg[1]
+    assert np.linalg.norm(Q.T @ Q - np.eye(Q.shape[1])) < 1e-8
+    assert np.linalg.norm(A @ Q - Q * eg[0][None, :]) < 1e-6
