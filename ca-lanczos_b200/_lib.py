@@ -71,6 +71,7 @@ SIGNATURES = {
                                                   C.c_int, C.c_int, c_dp, c_i64, C.POINTER(c_dp), c_dp, c_ip, c_ip]),
     "calz_dmma_peak": (C.c_int, [c_vp, c_dp]),
     "calz_block_axpy": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_i64, C.c_int, c_dp, c_vp, c_i64, c_vp, c_i64]),
+    "calz_orth_error": (C.c_int, [c_vp, c_i64, C.c_int, C.POINTER(c_vp), c_i64p, c_ip, C.c_int, C.c_int, c_dp]),
     "calz_gram": (C.c_int, [c_vp, c_i64, C.c_int, c_vp, c_i64, C.c_int, c_vp, c_i64, c_vp]),
 }
 

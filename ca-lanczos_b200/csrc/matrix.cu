@@ -20,7 +20,10 @@ namespace {
 // j in R_k, else -1.  Rows outside [row_begin,row_end) that would have to be expanded -> CALZ_ERR_CLOSURE.
 int level_sets_host(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_t row_end, const int64_t* rowptr,
                     const int32_t* colind, int64_t lo, int64_t hi, int s, std::vector<int8_t>& level,
-                    std::vector<std::vector<int64_t>>* by_level) {
+                    std::vector<std::vector<int64_t>>* by_level, int* covered = nullptr) {
+    // covered != NULL: instead of failing when a frontier row is not supplied, report the deepest level whose sets are
+    // complete (the caller then settles for a shallower ghost closure); levels beyond it are reset to -1.
+    if (covered) *covered = s;
     if (s > 120) return set_error(ctx, CALZ_ERR_BADARG, "s=%d too large", s);
     level.assign((size_t)n_glob, (int8_t)-1);
     for (int64_t i = lo; i < hi; ++i) level[i] = 0;
@@ -45,11 +48,21 @@ int level_sets_host(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_t ro
                 if (!expand(i)) return set_error(ctx, CALZ_ERR_CLOSURE, "owned row %lld not supplied", (long long)i);
             first = false;
         } else {
+            bool short_of_rows = false;
             for (int64_t i : frontier)
-                if (!expand(i))
-                    return set_error(ctx, CALZ_ERR_CLOSURE,
-                                     "row %lld (ghost level %d) is needed but rows [%lld,%lld) were supplied",
-                                     (long long)i, k - 1, (long long)row_begin, (long long)row_end);
+                if (!expand(i)) {
+                    if (!covered)
+                        return set_error(ctx, CALZ_ERR_CLOSURE,
+                                         "row %lld (ghost level %d) is needed but rows [%lld,%lld) were supplied",
+                                         (long long)i, k - 1, (long long)row_begin, (long long)row_end);
+                    short_of_rows = true;
+                    break;
+                }
+            if (short_of_rows) {                      // level k is incomplete: forget it
+                for (int64_t j : next) level[j] = (int8_t)-1;
+                *covered = k - 1;
+                break;
+            }
         }
         std::sort(next.begin(), next.end());
         if (by_level) (*by_level)[k] = next;
@@ -91,7 +104,8 @@ int calz_mat_destroy(calz_mat* m) {
     if (!m) return CALZ_OK;
     if (m->ctx) cudaStreamSynchronize(m->ctx->stream);
     p2p_halo_teardown(m);
-    void* ptrs[] = {m->d_xs_off, m->d_codes, m->d_dict, m->d_send_idx, m->d_send_buf, m->d_rowptr, m->d_colind, m->d_val, m->d_slice_ptr,
+    void* ptrs[] = {m->d_long_row, m->d_long_seg0, m->d_long_segptr, m->d_long_segrow, m->d_long_col, m->d_long_val, m->d_long_part,
+                    m->d_xs_off, m->d_codes, m->d_dict, m->d_send_idx, m->d_send_buf, m->d_rowptr, m->d_colind, m->d_val, m->d_slice_ptr,
                     m->d_sell_col, m->d_sell_val, m->d_perm, m->d_W_alloc};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -129,12 +143,55 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
         }
         m->n_loc = n_glob;
         m->own_off = 0;
+        m->halo_level = s_max;
     } else {
-        int st = level_sets_host(ctx, n_glob, row_begin, row_end, rowptr, colind, lo, hi, s_max, level, nullptr);
+        // ---- depth L of the ghost closure (= MPK steps per halo exchange).  Explicit ("mpk_halo_level") or automatic: the
+        //      deepest level the supplied rows cover whose ghost count does not exceed the owned rows (redundant work <= 2x),
+        //      minimised over the ranks so that everybody follows the same exchange schedule.
+        const int want = ctx->opt_mpk_halo_level > 0 ? (int)std::min<int64_t>(ctx->opt_mpk_halo_level, s_max) : s_max;
+        int covered = want;
+        int st = level_sets_host(ctx, n_glob, row_begin, row_end, rowptr, colind, lo, hi, want, level, nullptr,
+                                 ctx->opt_mpk_halo_level > 0 ? nullptr : &covered);
         if (st != CALZ_OK) {
             delete m;
             return st;
         }
+        int L = covered;
+        if (ctx->opt_mpk_halo_level <= 0) {
+            std::vector<int64_t> cnt(want + 2, 0);
+            for (int64_t j = 0; j < n_glob; ++j)
+                if (level[j] > 0) cnt[level[j]]++;
+            int64_t ghosts = 0;
+            int best = 1;
+            for (int k = 1; k <= covered; ++k) {
+                ghosts += cnt[k];
+                if (ghosts <= m->n_own) best = k;
+            }
+            L = std::max(1, std::min(best, covered));
+            if (covered < 1) {
+                delete m;
+                return set_error(ctx, CALZ_ERR_CLOSURE, "the owned rows [%lld,%lld) were not all supplied", (long long)lo, (long long)hi);
+            }
+        }
+        {   // min over the ranks (a P-vector of proposals through the small all-reduce)
+            std::vector<double> prop(P, 0.0);
+            prop[me] = (double)L;
+            double* d_prop = nullptr;
+            CALZ_CUDA(ctx, cudaMalloc(&d_prop, P * sizeof(double)));
+            CALZ_CUDA(ctx, cudaMemcpy(d_prop, prop.data(), P * sizeof(double), cudaMemcpyHostToDevice));
+            CALZ_TRY(allreduce_sum(ctx, d_prop, P));
+            CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            CALZ_CUDA(ctx, cudaMemcpy(prop.data(), d_prop, P * sizeof(double), cudaMemcpyDeviceToHost));
+            cudaFree(d_prop);
+            for (int q = 0; q < P; ++q) L = std::min(L, (int)prop[q]);
+        }
+        if (L < 1) {
+            delete m;
+            return set_error(ctx, CALZ_ERR_CLOSURE, "no common ghost-closure depth");
+        }
+        for (int64_t j = 0; j < n_glob; ++j)
+            if (level[j] > L) level[j] = (int8_t)-1;
+        m->halo_level = L;
         for (int64_t j = 0; j < lo; ++j)
             if (level[j] > 0) m->ghost_glob.push_back(j);
         m->own_off = (int64_t)m->ghost_glob.size();
@@ -157,13 +214,18 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
         return m->n_own + (std::lower_bound(m->ghost_glob.begin() + own_off, m->ghost_glob.end(), g) - m->ghost_glob.begin());
     };
 
-    // ---- local CSR: rows with level <= s_max-1 (level-s_max rows are only read, never computed)
+    // ---- local CSR: rows with level <= L-1 (level-L rows are only read, never computed).  Rows with more than kLongRow
+    //      entries go to the long-row structure instead (main row length 0).
+    const int HL = m->halo_level;
+    constexpr int64_t kLongRow = 2048, kLongSeg = 4096;
+    std::vector<int32_t> long_row, long_seg0(1, 0), long_segptr(1, 0), long_segrow;
+    std::vector<int64_t> long_len;
     std::vector<int64_t> h_rowptr64(n_loc + 1, 0);
     for (int64_t l = 0; l < n_loc; ++l) {
         int64_t g = loc_to_glob(l);
         int lev = (P == 1) ? 0 : level[g];
         int64_t cnt = 0;
-        if (lev <= s_max - 1) {
+        if (lev <= HL - 1) {
             if (g < row_begin || g >= row_end) {
                 delete m;
                 return set_error(ctx, CALZ_ERR_CLOSURE, "row %lld (level %d) needed but not supplied", (long long)g, lev);
@@ -173,18 +235,47 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
                 for (int64_t e = rowptr[g - row_begin]; e < rowptr[g - row_begin + 1]; ++e)
                     if (level[colind[e]] >= 0) ++cnt;
         }
+        if (cnt > kLongRow && n_loc < (int64_t)2147483647) {
+            long_row.push_back((int32_t)l);
+            long_len.push_back(cnt);
+            for (int64_t o = 0; o < cnt; o += kLongSeg) {
+                long_segrow.push_back((int32_t)long_row.size() - 1);
+                long_segptr.push_back(long_segptr.back() + (int32_t)std::min<int64_t>(kLongSeg, cnt - o));
+            }
+            long_seg0.push_back((int32_t)long_segrow.size());
+            cnt = 0;
+        }
         h_rowptr64[l + 1] = h_rowptr64[l] + cnt;
     }
-    m->nnz_loc = h_rowptr64[n_loc];
+    m->n_long = (int64_t)long_row.size();
+    m->n_long_seg = (int64_t)long_segrow.size();
+    const int64_t nnz_long = long_segptr.back();
+    m->nnz_loc = h_rowptr64[n_loc] + nnz_long;
     if (m->nnz_loc >= (int64_t)2147483647 || n_loc >= (int64_t)2147483647) {
         delete m;
         return set_error(ctx, CALZ_ERR_UNSUPPORTED, "local matrix too large for 32-bit indices (nnz_loc=%lld)", (long long)m->nnz_loc);
     }
     std::vector<int32_t> h_rowptr(n_loc + 1);
     for (int64_t l = 0; l <= n_loc; ++l) h_rowptr[l] = (int32_t)h_rowptr64[l];
-    std::vector<int32_t> h_col((size_t)m->nnz_loc);
-    std::vector<double> h_val((size_t)m->nnz_loc);
+    std::vector<int32_t> h_col((size_t)(m->nnz_loc - nnz_long));
+    std::vector<double> h_val((size_t)(m->nnz_loc - nnz_long));
+    std::vector<int32_t> lg_col((size_t)nnz_long);
+    std::vector<double> lg_val((size_t)nnz_long);
     int64_t bw = 0;
+    {   // long rows first (their main row length is 0)
+        for (size_t r = 0; r < long_row.size(); ++r) {
+            const int64_t l = long_row[r], g = loc_to_glob(l);
+            int64_t w = long_segptr[long_seg0[r]];
+            for (int64_t e = rowptr[g - row_begin]; e < rowptr[g - row_begin + 1]; ++e) {
+                int64_t jl = (P == 1) ? (int64_t)colind[e] : glob_to_loc(colind[e]);
+                if (jl < 0) continue;
+                lg_col[w] = (int32_t)jl;
+                lg_val[w] = val[e];
+                bw = std::max<int64_t>(bw, jl > l ? jl - l : l - jl);
+                ++w;
+            }
+        }
+    }
     for (int64_t l = 0; l < n_loc; ++l) {
         if (h_rowptr[l + 1] == h_rowptr[l]) continue;
         int64_t g = loc_to_glob(l);
@@ -204,7 +295,7 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
     m->hull_lo.assign(s_max + 1, 0);
     m->hull_hi.assign(s_max + 1, n_loc);
     if (P > 1) {
-        for (int L = 0; L <= s_max; ++L) {
+        for (int L = 0; L <= HL; ++L) {
             int64_t a = own_off, b = own_off + m->n_own;
             for (int64_t l = 0; l < own_off; ++l)
                 if (level[m->ghost_glob[l]] <= L) { a = l; break; }
@@ -502,6 +593,16 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
         if (!perm.empty()) CALZ_TRY(upload(ctx, &m->d_perm, perm));
     }
 
+    if (m->n_long) {
+        CALZ_TRY(upload(ctx, &m->d_long_row, long_row));
+        CALZ_TRY(upload(ctx, &m->d_long_seg0, long_seg0));
+        CALZ_TRY(upload(ctx, &m->d_long_segptr, long_segptr));
+        CALZ_TRY(upload(ctx, &m->d_long_segrow, long_segrow));
+        CALZ_TRY(upload(ctx, &m->d_long_col, lg_col));
+        CALZ_TRY(upload(ctx, &m->d_long_val, lg_val));
+        CALZ_CUDA(ctx, cudaMalloc(&m->d_long_part, (size_t)m->n_long_seg * sizeof(double)));
+    }
+
     // ---- basis workspace
     m->ldW = round_up(n_loc, 32);
     // The OWNED rows of every column must start 16-byte aligned on every rank (TMA bulk copies; and every rank has to take the
@@ -557,6 +658,8 @@ int calz_mat_info(const calz_mat* m, const char* what, int64_t* value) {
     else if (!strcmp(what, "n_ghost")) *value = m->n_loc - m->n_own;
     else if (!strcmp(what, "bandwidth")) *value = m->bandwidth;
     else if (!strcmp(what, "s_max")) *value = m->s_max;
+    else if (!strcmp(what, "halo_level")) *value = m->halo_level;
+    else if (!strcmp(what, "n_long_rows")) *value = m->n_long;
     else if (!strcmp(what, "ldW")) *value = m->ldW;
     else if (!strcmp(what, "dict_size")) *value = m->dict_size;
     else if (!strcmp(what, "dict_uniform_pct")) *value = (int64_t)(100.0 * m->dict_uniform);

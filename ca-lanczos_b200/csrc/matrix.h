@@ -7,7 +7,10 @@ struct calz_mat {
     int64_t n_glob = 0, row_lo = 0, row_hi = 0;      // owned global rows [row_lo,row_hi)
     int64_t n_own = 0, n_loc = 0, own_off = 0;       // local index space: ascending global index over R_s
     int64_t nnz_loc = 0, bandwidth = 0;
-    int s_max = 0;
+    int s_max = 0;                                   // columns of the basis workspace - 1
+    int halo_level = 0;                              // L: depth of the ghost closure = MPK steps per halo exchange (L = s_max is PA1:
+                                                     // one exchange per block; L = 1 is the classic per-step exchange, what a power-law
+                                                     // graph whose level-1 closure is already every row needs)
     int layout = CALZ_LAYOUT_CSR;
 
     std::vector<int64_t> ghost_glob;                 // sorted global indices of ghost_s(p)
@@ -27,12 +30,24 @@ struct calz_mat {
     std::vector<double*> peer_W;
     std::vector<void*> peer_W_base;                  // what cudaIpcOpenMemHandle returned (to close it)
     std::vector<long long> peer_dst_off;
+    std::vector<long long> peer_ldW;                 // leading dimension of the peer's workspace (pushes into column k > 0)
 
     // CSR (local indices)
     int32_t* d_rowptr = nullptr;
     int32_t* d_colind = nullptr;
     double* d_val = nullptr;
     int csr_lanes = 8;
+
+    // long rows (> kLongRow entries, power-law hubs): kept out of the main layout and processed by one CTA per segment of
+    // kLongSeg entries (deterministic two-stage sum), so that no warp of the main kernel crawls through a 10^6-entry row
+    int64_t n_long = 0, n_long_seg = 0;
+    int32_t* d_long_row = nullptr;                   // local row index per long row
+    int32_t* d_long_seg0 = nullptr;                  // first segment of long row r (n_long + 1 entries)
+    int32_t* d_long_segptr = nullptr;                // first entry of segment g (n_long_seg + 1 entries)
+    int32_t* d_long_segrow = nullptr;                // long-row slot of segment g
+    int32_t* d_long_col = nullptr;
+    double* d_long_val = nullptr;
+    double* d_long_part = nullptr;                   // per-segment partial sums
 
     // SELL-32-sigma (column-major inside a slice of 32 rows)
     int64_t sell_slices = 0, sell_padded = 0;
@@ -68,6 +83,6 @@ int launch_selld_ufast(calz_mat* m, const double* x, const double* xp, double* y
                        double pair);                                   // mpk_ufast.cu (experimental, opt-in)
 int p2p_halo_setup(calz_mat* m);
 void p2p_halo_teardown(calz_mat* m);
-int p2p_halo_exchange(calz_mat* m, double* w);
+int p2p_halo_exchange(calz_mat* m, double* w, int col);
 int p2p_halo_ack(calz_mat* m);
 }  // namespace calz

@@ -328,6 +328,45 @@ k_spmv_csr(const int32_t* __restrict__ rowptr, const int32_t* __restrict__ col, 
     }
 }
 
+// ---- long rows (hubs of a power-law graph): one CTA per segment of <= 4096 entries, fixed reduction order; then one thread per
+//      long row adds its segments in order and applies the epilogue.  Runs after the main kernel (which saw these rows as empty).
+__global__ void __launch_bounds__(256)
+k_spmv_long_seg(const int32_t* __restrict__ segptr, const int32_t* __restrict__ segrow, const int32_t* __restrict__ lrow,
+                const int32_t* __restrict__ col, const double* __restrict__ val, const double* __restrict__ x,
+                double* __restrict__ part, int lo, int hi) {
+    const int g = blockIdx.x;
+    const int row = __ldg(lrow + __ldg(segrow + g));
+    if (row < lo || row >= hi) return;
+    const int e0 = __ldg(segptr + g), e1 = __ldg(segptr + g + 1);
+    double sum = 0.0;
+    for (int e = e0 + threadIdx.x; e < e1; e += 256) sum = fma(__ldg(val + e), x[__ldg(col + e)], sum);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __shared__ double ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += ws[w];
+        part[g] = t;
+    }
+}
+
+template <bool NEWTON>
+__global__ void k_spmv_long_fin(int n_long, const int32_t* __restrict__ seg0, const int32_t* __restrict__ lrow,
+                                const double* __restrict__ part, const double* __restrict__ x, const double* __restrict__ xprev,
+                                double* __restrict__ y, int lo, int hi, double shift, double pair) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_long) return;
+    const int row = __ldg(lrow + r);
+    if (row < lo || row >= hi) return;
+    double sum = 0.0;
+    for (int g = __ldg(seg0 + r); g < __ldg(seg0 + r + 1); ++g) sum += part[g];
+    if (NEWTON) sum = newton_epilogue(sum, x[row], pair != 0.0 ? xprev[row] : 0.0, shift, pair);
+    y[row] = sum;
+}
+
 __global__ void k_pack(const double* __restrict__ x, const int32_t* __restrict__ idx, double* __restrict__ buf, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) buf[i] = x[idx[i]];
@@ -394,10 +433,32 @@ int launch_selld(calz_mat* m, const double* x, const double* xp, double* y, int6
 #undef CALZ_SELLD_CASE
 }
 
+int spmv_main(calz_mat* m, const double* x, const double* xp, double* y, int64_t lo, int64_t hi, bool newton, double shift, double pair);
+
 // one SpMV step on local rows [lo,hi) (already aligned to the layout granule)
 int spmv_step(calz_mat* m, const double* x, const double* xp, double* y, int64_t lo, int64_t hi, bool newton,
               double shift, double pair) {
     if (hi <= lo) return CALZ_OK;
+    CALZ_TRY(spmv_main(m, x, xp, y, lo, hi, newton, shift, pair));
+    if (m->n_long) {
+        calz_ctx* ctx = m->ctx;
+        k_spmv_long_seg<<<(unsigned)m->n_long_seg, 256, 0, ctx->stream>>>(m->d_long_segptr, m->d_long_segrow, m->d_long_row, m->d_long_col,
+                                                                          m->d_long_val, x, m->d_long_part, (int)lo, (int)hi);
+        CALZ_LAUNCH_CHECK(ctx);
+        const unsigned g = (unsigned)((m->n_long + 127) / 128);
+        if (newton)
+            k_spmv_long_fin<true><<<g, 128, 0, ctx->stream>>>((int)m->n_long, m->d_long_seg0, m->d_long_row, m->d_long_part, x, xp, y,
+                                                              (int)lo, (int)hi, shift, pair);
+        else
+            k_spmv_long_fin<false><<<g, 128, 0, ctx->stream>>>((int)m->n_long, m->d_long_seg0, m->d_long_row, m->d_long_part, x, xp, y,
+                                                               (int)lo, (int)hi, 0.0, 0.0);
+        CALZ_LAUNCH_CHECK(ctx);
+    }
+    return CALZ_OK;
+}
+
+int spmv_main(calz_mat* m, const double* x, const double* xp, double* y, int64_t lo, int64_t hi, bool newton,
+              double shift, double pair) {
     calz_ctx* ctx = m->ctx;
     if (m->layout == CALZ_LAYOUT_SELL_DICT && m->xs_rows > 0 && ctx->opt_mpk_tma_x && m->W_pad == 0) {   // bulk copies need 16-B aligned x segments
         const int64_t s0 = lo / 32, s1 = (hi + 31) / 32;
@@ -437,12 +498,13 @@ int spmv_step(calz_mat* m, const double* x, const double* xp, double* y, int64_t
     return newton ? launch_csr<true>(m, x, xp, y, lo, hi, shift, pair) : launch_csr<false>(m, x, xp, y, lo, hi, 0.0, 0.0);
 }
 
-// the ONE level-s halo exchange of an outer step: column `col` of the workspace
-int halo_exchange(calz_mat* m, double* w) {
+// one level-L halo exchange of workspace column `col` (L = s: the ONE exchange of an outer step, the communication-avoiding point)
+int halo_exchange(calz_mat* m, double* W, int col) {
     calz_ctx* ctx = m->ctx;
     const int P = ctx->nranks;
     if (P <= 1) return CALZ_OK;
-    if (m->p2p_halo) return p2p_halo_exchange(m, w);      // push into the peers' ghost zones over NVLink (p2p.cu)
+    if (m->p2p_halo) return p2p_halo_exchange(m, W, col);      // push into the peers' ghost zones over NVLink (p2p.cu)
+    double* w = W + (int64_t)col * m->ldW;
     for (int q = 0; q < P; ++q)
         if (m->send_cnt[q] && !m->send_contig[q]) {
             const int64_t n = m->send_cnt[q];
@@ -499,11 +561,25 @@ int mpk_run(calz_mat* m, const double* v, int s, const Shifts& sh) {
     const int64_t ld = m->ldW;
     if (v != W + m->own_off)
         CALZ_CUDA(ctx, cudaMemcpyAsync(W + m->own_off, v, (size_t)m->n_own * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    CALZ_TRY(halo_exchange(m, W));
+    const int P = ctx->nranks;
+    const int L = (P > 1) ? std::max(1, std::min(m->halo_level, s)) : s;      // steps per halo exchange
 
     const int64_t gran = (m->layout == CALZ_LAYOUT_SELL) ? (m->d_perm ? m->sell_sigma : 32) : (m->layout == CALZ_LAYOUT_SELL_DICT ? 32 : 1);
-    auto lo_of = [&](int k) { return (m->hull_lo[s - k] / gran) * gran; };
-    auto hi_of = [&](int k) { return std::min<int64_t>(m->n_loc, round_up(m->hull_hi[s - k], gran)); };
+    // step k is the j-th of its exchange group: it has to produce the rows up to level min(L - j, s - k)
+    auto lev_of = [&](int k) { return std::min(L - ((k - 1) % L + 1), s - k); };
+    auto lo_of = [&](int k) { return (m->hull_lo[lev_of(k)] / gran) * gran; };
+    auto hi_of = [&](int k) { return std::min<int64_t>(m->n_loc, round_up(m->hull_hi[lev_of(k)], gran)); };
+    auto exchange_before = [&](int k) -> int {
+        if ((k - 1) % L != 0) return CALZ_OK;
+        // the conjugate-pair term of step k reads column k-2 on the ghost rows too, and the last step of the previous group
+        // only produced its owned rows
+        if (k >= 2 && sh.pair[k - 1] != 0.0) CALZ_TRY(halo_exchange(m, W, k - 2));
+        return halo_exchange(m, W, k - 1);
+    };
+    auto ack_after = [&](int k) -> int {
+        if (m->p2p_halo && (k - 1) % L == 0) return p2p_halo_ack(m);       // ghosts consumed: the owners may push the next ones
+        return CALZ_OK;
+    };
     auto step = [&](int k, int64_t lo, int64_t hi) -> int {
         lo = std::max(lo, lo_of(k));
         hi = std::min(hi, hi_of(k));
@@ -517,13 +593,18 @@ int mpk_run(calz_mat* m, const double* v, int s, const Shifts& sh) {
     const int64_t bytes_per_row = m->n_loc ? (12 * m->nnz_loc) / m->n_loc + 24 : 0;
     const int64_t bwid = round_up(std::max<int64_t>(m->bandwidth, 1), gran);
     int64_t chunk_rows = 0;
-    if (ctx->opt_l2_chunk_bytes > 0 && bytes_per_row > 0) {
+    if (ctx->opt_l2_chunk_bytes > 0 && bytes_per_row > 0 && L >= s) {
         chunk_rows = round_up(std::max<int64_t>(ctx->opt_l2_chunk_bytes / bytes_per_row, gran), gran);
         if (chunk_rows < 2 * bwid || chunk_rows >= m->n_loc) chunk_rows = 0;   // band too wide / matrix fits: plain sweeps
     }
     if (chunk_rows == 0) {
-        for (int k = 1; k <= s; ++k) CALZ_TRY(step(k, 0, m->n_loc));
+        for (int k = 1; k <= s; ++k) {
+            CALZ_TRY(exchange_before(k));
+            CALZ_TRY(step(k, 0, m->n_loc));
+            CALZ_TRY(ack_after(k));
+        }
     } else {
+        CALZ_TRY(exchange_before(1));
         const int64_t span = m->n_loc + (int64_t)(s - 1) * bwid;
         for (int64_t c0 = 0; c0 < span; c0 += chunk_rows)
             for (int k = 1; k <= s; ++k) {
@@ -531,8 +612,8 @@ int mpk_run(calz_mat* m, const double* v, int s, const Shifts& sh) {
                 if (hi <= 0 || lo >= m->n_loc) continue;
                 CALZ_TRY(step(k, std::max<int64_t>(lo, 0), std::min<int64_t>(hi, m->n_loc)));
             }
+        CALZ_TRY(ack_after(1));
     }
-    if (m->p2p_halo) CALZ_TRY(p2p_halo_ack(m));           // column-0 ghosts consumed: the owners may push the next ones
     return CALZ_OK;
 }
 

@@ -127,6 +127,68 @@ int calz_block_axpy(calz_ctx* ctx, int64_t n, int m, const double* Q, int64_t ld
     return ts_update(ctx, n, Q, ldQ, m, sm, m, X, X ? ldX : 0, c, Y, ldY, nullptr, 0);
 }
 
+int calz_orth_error(calz_ctx* ctx, int64_t n, int nblk, const double* const* Qblk, const int64_t* ldQ, const int* mcols, int mode,
+                    int s, double* err) {
+    if (!ctx || !err || n < 1 || nblk < 1 || !Qblk || !ldQ || !mcols || (mode != CALZ_ORTH_FRO && mode != CALZ_ORTH_LASTBLOCK))
+        return set_error(ctx, CALZ_ERR_BADARG, "calz_orth_error: bad arguments");
+    CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    // virtual column j of Q -> (pointer, ld)
+    std::vector<const double*> colp;
+    for (int i = 0; i < nblk; ++i)
+        if (!empty_block(Qblk, mcols, i))
+            for (int j = 0; j < mcols[i]; ++j) colp.push_back(Qblk[i] + (size_t)j * ldQ[i]);
+    const int tot = (int)colp.size();
+    if (tot == 0) { *err = 0.0; return CALZ_OK; }
+    // runs of columns that are contiguous in memory with one leading dimension (a block is one run)
+    struct Run { const double* p; int64_t ld; int c0, nc; };
+    std::vector<Run> runs;
+    {
+        int c0 = 0;
+        for (int i = 0; i < nblk; ++i)
+            if (!empty_block(Qblk, mcols, i)) { runs.push_back({Qblk[i], ldQ[i], c0, mcols[i]}); c0 += mcols[i]; }
+    }
+    // G(:, cols of B-chunk) = Q' * B-chunk, B-chunks of <= 32 columns inside one run; only the column range the mode needs
+    const int jlo = (mode == CALZ_ORTH_LASTBLOCK && tot > s + 1) ? tot - s - 1 : 0;
+    std::vector<double> G((size_t)tot * tot, 0.0);
+    double* sm;
+    CALZ_TRY(small_scratch(ctx, (size_t)tot * 32, &sm));
+    for (const Run& rb : runs) {
+        for (int b0 = 0; b0 < rb.nc; b0 += 32) {
+            const int cb = std::min(32, rb.nc - b0);
+            if (rb.c0 + b0 + cb <= jlo) continue;
+            const double* B = rb.p + (size_t)b0 * rb.ld;
+            // A side: up to 4 runs per launch (Panels), rows of G at the run's column offset
+            for (size_t r0 = 0; r0 < runs.size(); r0 += 4) {
+                Panels A{};
+                int a_c0 = runs[r0].c0;
+                for (size_t r = r0; r < std::min(runs.size(), r0 + 4); ++r) add_panel(A, runs[r].p, runs[r].ld, runs[r].nc);
+                CALZ_TRY(tsmm_tn(ctx, n, A, B, rb.ld, cb, sm, A.total, false, nullptr, 0, true));
+                CALZ_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, sm, (size_t)A.total * cb * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+                CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                for (int j = 0; j < cb; ++j)
+                    for (int a = 0; a < A.total; ++a) G[(size_t)(rb.c0 + b0 + j) * tot + a_c0 + a] = ctx->pinned[(size_t)j * A.total + a];
+            }
+        }
+    }
+    double e = 0.0;
+    if (mode == CALZ_ORTH_FRO) {
+        for (int j = 0; j < tot; ++j)
+            for (int i = 0; i < tot; ++i) {
+                const double d = (i == j ? 1.0 : 0.0) - G[(size_t)j * tot + i];
+                e += d * d;
+            }
+        e = sqrt(e);
+    } else if (tot > s + 1) {
+        for (int j = tot - s - 1; j < tot; ++j)
+            for (int i = 0; i < tot - s - 1; ++i) e = std::max(e, fabs(G[(size_t)j * tot + i]));
+    } else {
+        for (int j = 0; j < tot; ++j)
+            for (int i = 0; i < tot; ++i) e = std::max(e, fabs(G[(size_t)j * tot + i] - (i == j ? 1.0 : 0.0)));
+    }
+    *err = e;
+    return CALZ_OK;
+}
+
 int calz_cholqr(calz_ctx* ctx, int64_t n, int c, const double* X, int64_t ldX, double* Q, int64_t ldQ, double* R, int* info) {
     if (!ctx || !X || !Q || !R || n < 1 || c < 1 || c > kMaxC) return set_error(ctx, CALZ_ERR_BADARG, "calz_cholqr: bad arguments");
     CALZ_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -248,10 +248,11 @@ int p2p_halo_setup(calz_mat* m) {
     m->p2p_halo = false;
     if (!ctx->p2p.enabled) return CALZ_OK;
     const int P = ctx->nranks;
-    struct Blob { cudaIpcMemHandle_t h; long long recv_off[kMaxPeers]; int ok; int w_pad; } blob;
+    struct Blob { cudaIpcMemHandle_t h; long long recv_off[kMaxPeers]; long long ldW; int ok; int w_pad; } blob;
     memset(&blob, 0, sizeof(blob));
     cudaError_t e = cudaIpcGetMemHandle(&blob.h, m->d_W_alloc);
     blob.w_pad = m->W_pad;
+    blob.ldW = m->ldW;
     blob.ok = (e == cudaSuccess);
     if (!blob.ok) cudaGetLastError();
     for (int q = 0; q < P; ++q) blob.recv_off[q] = m->recv_off[q];
@@ -262,6 +263,7 @@ int p2p_halo_setup(calz_mat* m) {
     m->peer_W.assign(P, nullptr);
     m->peer_W_base.assign(P, nullptr);
     m->peer_dst_off.assign(P, 0);
+    m->peer_ldW.assign(P, 0);
     for (int q = 0; q < P && all_ok; ++q) {
         if (q == ctx->rank || (m->send_cnt[q] == 0 && m->recv_cnt[q] == 0)) continue;
         void* ptr = nullptr;
@@ -270,6 +272,7 @@ int p2p_halo_setup(calz_mat* m) {
         m->peer_W[q] = (double*)ptr + ((Blob*)all[q].data())->w_pad;      // the peer's d_W (its allocation + alignment shift)
         m->peer_W_base[q] = ptr;
         m->peer_dst_off[q] = ((Blob*)all[q].data())->recv_off[ctx->rank];      // where q receives MY rows
+        m->peer_ldW[q] = ((Blob*)all[q].data())->ldW;
     }
     double verdict = all_ok ? 0.0 : 1.0, *d_v = nullptr;
     CALZ_CUDA(ctx, cudaMalloc(&d_v, sizeof(double)));
@@ -291,8 +294,9 @@ void p2p_halo_teardown(calz_mat* m) {
     m->peer_W_base.clear();
 }
 
-// push my boundary rows of workspace column 0 into the peers' ghost zones, wait for theirs
-int p2p_halo_exchange(calz_mat* m, double* w) {
+// push my boundary rows of workspace column `col` into the peers' ghost zones (same column), wait for theirs
+int p2p_halo_exchange(calz_mat* m, double* W, int col) {
+    const double* w = W + (long long)col * m->ldW;
     calz_ctx* ctx = m->ctx;
     P2P& p = ctx->p2p;
     const int P = ctx->nranks;
@@ -305,7 +309,7 @@ int p2p_halo_exchange(calz_mat* m, double* w) {
         if (q != ctx->rank && m->send_cnt[q]) {
             const int k = h.npeer++;
             h.peer[k] = q;
-            h.dst[k] = m->peer_W[q] + m->peer_dst_off[q];
+            h.dst[k] = m->peer_W[q] + (long long)col * m->peer_ldW[q] + m->peer_dst_off[q];
             h.idx[k] = m->send_contig[q] ? nullptr : m->d_send_idx + m->send_off[q];
             h.src_off[k] = m->own_off + (m->send_glob[q][0] - m->row_lo);
             h.count[k] = m->send_cnt[q];

@@ -106,6 +106,53 @@ def powerlaw_spd(n: int, avg_deg: float = 20.0, seed: int = 0, alpha: float = 0.
     return A
 
 
+def powerlaw_spd_rows(n: int, avg_deg: float = 20.0, seed: int = 0, alpha: float = 0.8, row_lo: int = 0, row_hi: int | None = None,
+                      shuffle: bool = True, chunk: int = 1 << 23) -> sp.csr_matrix:
+    """Rows [row_lo,row_hi) of the C4 matrix at scale (n = 2e7, nnz ~ 4e8), generated WITHOUT the other rows: the edge
+    list is produced chunk by chunk from a counter-seeded generator (every rank generates the same chunks and keeps the
+    edges that touch its rows), so host memory stays bounded by the rank's own share.
+
+    Edges (i,j): i = pi(floor(n*u^(1/(1-alpha)))) -- the continuous inverse CDF of weights rank^-alpha -- j uniform, values
+    -U(0,1) on a 2^-30 grid (sums of duplicates and of whole rows are then exact, i.e. independent of the order in which a
+    rank meets the edges: the matrix is exactly symmetric and exactly the same for every partition), symmetrised, duplicates summed, diagonal = sum|row| + 1 (strictly diagonally dominant => SPD).  ``shuffle``
+    relabels the vertices by the affine permutation pi(r) = (a*r + b) mod n (a coprime to n): the spectrum is unchanged, but
+    the hubs are spread over the row partition instead of all landing on rank 0 (the contiguous-block partition of the north
+    star is fixed; a power-law graph in degree order would put ~40 % of the non-zeros on the first of 8 ranks)."""
+    n = int(n)
+    row_hi = n if row_hi is None else int(row_hi)
+    m = int(n * avg_deg / 2)
+    a_mul = 0
+    if shuffle:
+        a_mul = int(0.6180339887 * n) | 1
+        while np.gcd(a_mul, n) != 1:
+            a_mul += 2
+    b_add = n // 3
+    rows, cols, vals = [], [], []
+    expo = 1.0 / (1.0 - alpha)
+    for c0 in range(0, m, chunk):
+        cnt = min(chunk, m - c0)
+        rng = np.random.default_rng([int(seed), c0 // chunk])
+        i = np.minimum((n * rng.random(cnt) ** expo).astype(np.int64), n - 1)
+        j = rng.integers(0, n, size=cnt, dtype=np.int64)
+        v = -(rng.integers(1, 1 << 30, size=cnt, dtype=np.int64).astype(np.float64) * (1.0 / (1 << 30)))
+        if shuffle:
+            i = (i * a_mul + b_add) % n
+        keep = i != j
+        mi = keep & (i >= row_lo) & (i < row_hi)
+        mj = keep & (j >= row_lo) & (j < row_hi)
+        rows += [i[mi], j[mj]]; cols += [j[mi], i[mj]]; vals += [v[mi], v[mj]]
+    rows = np.concatenate(rows) - row_lo; cols = np.concatenate(cols); vals = np.concatenate(vals)
+    B = sp.coo_matrix((vals, (rows, cols)), shape=(row_hi - row_lo, n)).tocsr()      # sums duplicates
+    del rows, cols, vals
+    d = -np.asarray(B.sum(axis=1)).ravel() + 1.0                                     # all off-diagonal values are negative
+    nloc = row_hi - row_lo
+    D = sp.csr_matrix((d, np.arange(row_lo, row_hi, dtype=np.int64), np.arange(nloc + 1, dtype=np.int64)), shape=(nloc, n))
+    A = (B + D).tocsr()
+    A.sort_indices()
+    A.indices = A.indices.astype(np.int32)
+    return A
+
+
 def _splitmix64(x: np.ndarray) -> np.ndarray:
     x = (x + np.uint64(0x9E3779B97F4A7C15))
     z = x

@@ -8,9 +8,9 @@ the GPU (restarted_ca_lanczos.m:4-202 'local' and 'full'; lanczos_basic :288-367
 implementation on the CPU and compare it with the oracle's restatement of the reference).  The O(m^3) host algebra (eig of
 the non-symmetric T, the lock-and-sort of converged pairs, the T assembly of :336-359) follows the reference line by line.
 
-STATUS: the control flow is covered by CPU tests (tests/test_restart_host.py); :class:`DeviceOps` only chains C-ABI calls
-that the GPU parity tests already cover one by one, but the end-to-end device run is still gated behind
-CALZ_TEST_EXPERIMENTAL=1 (written after the GPU budget of round 1 was spent).
+The control flow is covered by CPU tests (tests/test_restart_host.py, numpy block operations vs the oracle);
+:class:`DeviceOps` chains C-ABI calls only and is checked end to end on the GPU by
+tests/test_gpu_driver.py::test_device_resident_restarted_ca_lanczos and by ``bench.py --config c4``.
 """
 from __future__ import annotations
 
@@ -186,6 +186,9 @@ def restarted_ca_lanczos(ops, r, max_lanczos, n_wanted_eigs=10, s=6, basis="newt
             rnorms[num_restarts - 1, nconv + i + k] = relres(rest[ix[i]], x)
         if want_orth_err:                                                              # :165-168  ||I - [Qc Qnew]'[Qc Qnew]||_F
             parts = ([Qc] if Qc is not None else []) + [Qm]
+            if hasattr(ops, "orth_fro"):
+                orth_err.append(ops.orth_fro(parts))
+                parts = []
             tot = sum(ops.ncols(p) for p in parts)
             G = np.zeros((tot, tot))
             o1 = 0
@@ -195,7 +198,8 @@ def restarted_ca_lanczos(ops, r, max_lanczos, n_wanted_eigs=10, s=6, basis="newt
                     G[o1:o1 + ops.ncols(p1), o2:o2 + ops.ncols(p2)] = ops.gram(p1, p2)
                     o2 += ops.ncols(p2)
                 o1 += ops.ncols(p1)
-            orth_err.append(float(np.linalg.norm(np.eye(tot) - G, "fro")))
+            if parts:
+                orth_err.append(float(np.linalg.norm(np.eye(tot) - G, "fro")))
         nconv += k
         restart = not (len(conv_eigs) >= n_wanted_eigs)                                # :178-181
         if restart:
@@ -225,7 +229,7 @@ class _Blk:
 class DeviceOps:
     """The block operations on the GPU: every method is one or a few C-ABI calls on the context's stream."""
 
-    def __init__(self, dm, backend="tsqr", A_host=None):
+    def __init__(self, dm, backend="tsqr", A_host=None, colsum=None):
         import torch
         from . import _lib
         self.torch, self._lib, self.dm, self.ctx, self.lib = torch, _lib, dm, dm.ctx, dm.ctx.lib
@@ -233,7 +237,9 @@ class DeviceOps:
         self.ld = (self.n + 31) // 32 * 32
         self.dev = torch.device("cuda", self.ctx.device)
         self.backend = backend
-        self._colsum = None if A_host is None else np.asarray(abs(A_host).sum(axis=0)).ravel().astype(np.float64)
+        # normest starts from the column sums of |A| (owned rows of this rank; A symmetric => the row sums of the owned rows)
+        self._colsum = (np.ascontiguousarray(colsum, dtype=np.float64) if colsum is not None else
+                        None if A_host is None else np.asarray(abs(A_host).sum(axis=0)).ravel().astype(np.float64))
         self._g = torch.zeros(16 * 16, dtype=torch.float64, device=self.dev)
         torch.cuda.synchronize(self.dev)
 
@@ -294,6 +300,11 @@ class DeviceOps:
 
     def nrm2(self, x):
         return float(np.sqrt(self.gram(x, x)[0, 0]))
+
+    def orth_fro(self, parts):
+        """norm(eye - [parts]'*[parts], 'fro')  (restarted_ca_lanczos.m:165-168) in one device pass"""
+        from .solver import orth_error
+        return orth_error(self.ctx, self.n, [(p.ptr, p.ld, p.cols) for p in parts], "fro")
 
     def abs_colsum(self, out):
         if self._colsum is None:

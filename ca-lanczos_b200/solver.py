@@ -181,6 +181,27 @@ def ca_lanczos(A, r, s, iter, basis="newton", orth="local", backend="cholqr2", c
     return eng.T_matrix(), eng.Q_host()
 
 
+# ----------------------------------------------------------------------------------------------- orthogonality (N2)
+def orth_error(ctx: Context, n: int, blocks, mode: str = "fro", s: int = 0) -> float:
+    """Loss of orthogonality of the device-resident basis [Q_1 ... Q_k] (``blocks``: (device pointer, ld, columns) triples):
+    ``mode='fro'``  norm(eye - Q'*Q,'fro') as restarted_ca_lanczos.m:165-168; ``mode='lastblock'`` compute_orth_err(Q,s) of
+    ca_lanczos.m:99-107 (max |Q_old' * Q_lastblock|).  One pass of DMMA Gram products (calz_orth_error), all-reduced."""
+    nb = len(blocks)
+    qb = (C.c_void_p * nb)(*[int(b[0]) for b in blocks])
+    lds = (C.c_int64 * nb)(*[int(b[1]) for b in blocks])
+    mc = (C.c_int * nb)(*[int(b[2]) for b in blocks])
+    err = C.c_double()
+    check(ctx.lib.calz_orth_error(ctx.h, int(n), nb, qb, lds, mc, {"fro": 0, "lastblock": 1}[mode], int(s), C.byref(err)), ctx.h)
+    return float(err.value)
+
+
+def engine_orth_errors(eng: BlockEngine):
+    """(compute_orth_err of ca_lanczos.m:99-107, ||I - Q'Q||_F) of everything the engine has produced so far."""
+    cols = eng.s * eng.k + 1
+    blk = [(eng._qcol(0), eng.ld, cols)]
+    return (orth_error(eng.ctx, eng.n, blk, "lastblock", eng.s), orth_error(eng.ctx, eng.n, blk, "fro"))
+
+
 # ----------------------------------------------------------------------------------------------- Ritz pairs (N1, N2)
 def ritz_residuals(eng: BlockEngine, nev: int | None = None):
     """compute_ritz_rnorm of ca_lanczos.m:88-97 on the device: Ritz values of T (general eig, T is not exactly

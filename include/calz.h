@@ -182,6 +182,16 @@ int  calz_gram(calz_ctx* ctx, int64_t n, int m, const double* A, int64_t ldA, in
  * vector assembly Q*Vp of restarted_ca_lanczos.m:135-139 / ca_lanczos.m:94 (pass C = -Vp, X = NULL). */
 int  calz_block_axpy(calz_ctx* ctx, int64_t n, int m, const double* Q, int64_t ldQ, int c, const double* C_host,
                      const double* X, int64_t ldX, double* Y, int64_t ldY);
+/* Orthogonality diagnostics of the drivers on the device; blocks as in calz_project (device pointers, the
+ * virtual matrix Q = [Q_1 ... Q_nblk] has `tot` columns).  One pass of DMMA Gram products, all-reduced; the tot x tot
+ * arithmetic is done on the host.
+ *   CALZ_ORTH_FRO        norm(eye(tot) - Q'*Q, 'fro')                          restarted_ca_lanczos.m:165-168
+ *   CALZ_ORTH_LASTBLOCK  compute_orth_err(Q, s) of ca_lanczos.m:99-107: tot > s+1: max|Q(:,1:tot-s-1)'*Q(:,tot-s:tot)|,
+ *                        else max|Q'*Q - eye(s+1)|  */
+#define CALZ_ORTH_FRO        0
+#define CALZ_ORTH_LASTBLOCK  1
+int  calz_orth_error(calz_ctx* ctx, int64_t n, int nblk, const double* const* Qblk, const int64_t* ldQ, const int* mcols,
+                     int mode, int s, double* err);
 /* measured peak of the fp64 tensor pipe (register-resident mma.sync.m8n8k4.f64 chains), TFLOP/s: the denominator of
  * the Gram kernels' "fraction of the fp64 tensor pipe" */
 int  calz_dmma_peak(calz_ctx* ctx, double* tflops);

@@ -69,20 +69,44 @@ def local_problem(A, lo, hi, s):
     return A_loc, loc2glob, level[loc2glob], own_off
 
 
-def mpk_partitioned(A, v, s, lam, P, basis="newton"):
-    """P-way redundant-ghost MPK (PA1): every rank gets v on R_s(p) once, runs the s steps on its local
-    matrix with no further exchange, and keeps the owned rows.  Returns the assembled n x (s+1) basis
-    (first column v for both bases)."""
+def choose_halo_level(A, P, s):
+    """Depth L of the ghost closure = MPK steps per halo exchange, as the library picks it when all rows are supplied:
+    per rank the deepest level <= s whose cumulative ghost count does not exceed the owned rows (at least 1), then the
+    minimum over the ranks.  L = s is PA1 (one exchange per block, stencils); L = 1 the per-step exchange (power-law)."""
     n = A.shape[0]
     b = row_bounds(n, P)
-    V = np.zeros((n, s + 1), order="F")
+    L = s
     for p in range(P):
         lo, hi = int(b[p]), int(b[p + 1])
-        A_loc, l2g, lev, off = local_problem(A, lo, hi, s)
-        v_loc = v[l2g]                                   # the ONE halo exchange
-        if basis == "newton":
-            V_loc = kernels.matrix_powers_newton(A_loc, v_loc, s, lam, 1)
-        else:
-            V_loc = np.column_stack([v_loc, kernels.matrix_powers_monomial(A_loc, v_loc, s)])
-        V[lo:hi, :] = V_loc[off : off + (hi - lo), :]
+        level = level_sets(A, lo, hi, s)
+        best, ghosts = 1, 0
+        for k in range(1, s + 1):
+            ghosts += int(np.count_nonzero(level == k))
+            if ghosts <= hi - lo:
+                best = k
+        L = min(L, best)
+    return max(L, 1)
+
+
+def mpk_partitioned(A, v, s, lam, P, basis="newton", halo_level=None):
+    """P-way redundant-ghost MPK.  ``halo_level`` = L (default s = PA1): every rank gets the current basis vector on
+    R_L(p), runs L steps on its local matrix with no further exchange (step j of a group on the rows of level <= L-j),
+    keeps the owned rows, and exchanges again.  Returns the assembled n x (s+1) basis (first column v for both bases)."""
+    n = A.shape[0]
+    L = s if halo_level is None else max(1, min(int(halo_level), s))
+    b = row_bounds(n, P)
+    V = np.zeros((n, s + 1), order="F")
+    V[:, 0] = v
+    lam = None if lam is None else np.asarray(lam)
+    for k0 in range(0, s, L):                            # steps k0+1 .. k0+g
+        g = min(L, s - k0)
+        for p in range(P):
+            lo, hi = int(b[p]), int(b[p + 1])
+            A_loc, l2g, lev, off = local_problem(A, lo, hi, L)
+            v_loc = V[l2g, k0]                           # the halo exchange of column k0
+            if basis == "newton":
+                V_loc = kernels.matrix_powers_newton(A_loc, v_loc, g, lam[k0:k0 + g], 1)
+            else:
+                V_loc = np.column_stack([v_loc, kernels.matrix_powers_monomial(A_loc, v_loc, g)])
+            V[lo:hi, k0 + 1:k0 + g + 1] = V_loc[off:off + (hi - lo), 1:g + 1]
     return V

@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--backend", default="cholqr2")
     ap.add_argument("--layout", default="auto")
     ap.add_argument("--matrix", default="lap3d", choices=["lap3d", "powerlaw"])
+    ap.add_argument("--halo-level", type=int, default=0, help="force the ghost-closure depth L (MPK steps per exchange); 0 = automatic")
+    ap.add_argument("--own-rows-only", action="store_true", help="supply only the owned rows (forces L = 1, what the C4 bench does)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -39,6 +41,8 @@ def main():
     ids = [api.Context.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     ctx.init_comm(world, rank, ids[0])
+    if args.halo_level:
+        ctx.set_option("mpk_halo_level", args.halo_level)
 
     m, s = args.grid, args.s
     mz = args.gridz or m
@@ -56,6 +60,9 @@ def main():
         lo, hi = (rank * n) // world, ((rank + 1) * n) // world
         have_lo, have_hi = 0, n
         A_rows = A
+    if args.own_rows_only:
+        have_lo, have_hi = lo, hi
+        A_rows = A[lo:hi]
     dm = api.DeviceMatrix(A_rows, s_max=s, layout=args.layout, ctx=ctx, n_glob=n, row_begin=have_lo)
     fails = []
 
@@ -67,9 +74,13 @@ def main():
     from oracle import partition
     b = partition.row_bounds(n, world)
     check("row bounds", (dm.info("row_lo"), dm.info("row_hi")) == (int(b[rank]), int(b[rank + 1])))
-    ghosts = partition.ghost_indices(A, lo, hi, s)
+    # depth of the ghost closure: forced, 1 when only the owned rows were supplied, else the oracle's restatement of the automatic rule
+    L = dm.info("halo_level")
+    L_want = min(args.halo_level, s) if args.halo_level else (1 if args.own_rows_only else partition.choose_halo_level(A, world, s))
+    check("halo level", L == L_want, "%d vs %d" % (L, L_want))
+    ghosts = partition.ghost_indices(A, lo, hi, L)
     check("ghost set", np.array_equal(dm.ghost_indices(), ghosts), "%d vs %d" % (dm.ghost_indices().size, ghosts.size))
-    lists = partition.exchange_lists(A, world, s)
+    lists = partition.exchange_lists(A, world, L)
     for q in range(world):
         check("recv list from %d" % q, np.array_equal(dm.recv_list(q), lists[rank][q]))
         check("send list to %d" % q, np.array_equal(dm.send_list(q), lists[q][rank]))
@@ -84,11 +95,12 @@ def main():
         To, Qo = drivers.ca_lanczos(A, r, s, s * args.blocks, "newton", "local", Bk=Bk, info=io)
         qtol = 1e-10
     else:
-        # shifts from the oracle's own 2s-step Lanczos + Leja ordering (ca_lanczos.m:66-71); 'local' orthogonalisation keeps
-        # ||I-Q'Q|| ~ 1e-6 on this matrix, so two backward-stable QRs agree to ~1e-6 in Q (1 GPU: 5e-6) and ~1e-11 in T
+        # shifts from the oracle's own 2s-step Lanczos + Leja ordering (ca_lanczos.m:66-71).  'local' orthogonalisation lets
+        # ||I-Q'Q|| grow to ~1e-6 on this matrix, so the ACCUMULATED trajectories of two backward-stable implementations drift
+        # apart by that much; the basis vectors are therefore compared per block from identical inputs below (1e-10).
         To, Qo = drivers.ca_lanczos(A, r, s, s * args.blocks, "newton", "local", info=io)
         shifts = np.diag(io["Bk"])[:s].copy()
-        qtol = 2e-5
+        qtol = None
     q0 = (r / np.sqrt(r @ r))[lo:hi]
     eng = BlockEngine(dm, s, args.blocks + 1, "newton", shifts, args.backend)
     eng.first_block(q0)
@@ -102,11 +114,38 @@ def main():
     ro = np.sort(np.linalg.eig(To)[0].real)[::-1]; rg = np.sort(np.linalg.eig(T)[0].real)[::-1]
     check("ritz 1e-8", np.max(np.abs(rg[:4] - ro[:4]) / np.abs(ro[:4])) < 1e-8)
     err = np.max(np.linalg.norm(Qloc - Qo[lo:hi, : Qloc.shape[1]], axis=0))
-    check("Q rows %.0e" % qtol, err < qtol, "%.3e" % err)
+    if qtol is not None:
+        check("Q trajectory %.0e" % qtol, err < qtol, "%.3e" % err)
+    # ---- per block, from IDENTICAL inputs (the oracle's Qprev and its MPK output): basis vectors within 1e-10 (north_star)
+    import ctypes as C
+    from ca_lanczos_b200 import _lib
+    ld = eng.ld
+    blk_err = 0.0
+    for k in range(2, args.blocks + 1):
+        Vo_k = kernels.matrix_powers_newton(A, Qo[:, (k - 1) * s], s, shifts, 1)
+        Qp = torch.zeros((s + 1, ld), dtype=torch.float64, device=dev)
+        Xd = torch.zeros((s, ld), dtype=torch.float64, device=dev)
+        Zd = torch.zeros((s, ld), dtype=torch.float64, device=dev)
+        Qp[:, : hi - lo] = torch.as_tensor(np.ascontiguousarray(Qo[lo:hi, (k - 2) * s:(k - 1) * s + 1].T), device=dev)
+        Xd[:, : hi - lo] = torch.as_tensor(np.ascontiguousarray(Vo_k[lo:hi, 1:].T), device=dev)
+        torch.cuda.synchronize(dev)
+        qb = (C.c_void_p * 1)(Qp.data_ptr()); lds = (C.c_int64 * 1)(ld); mc = (C.c_int * 1)(s + 1)
+        R1 = np.zeros((s + 1, s), order="F"); Rl = np.zeros((s, s), order="F")
+        rp = (_lib.c_dp * 1)(R1.ctypes.data_as(_lib.c_dp))
+        sec, rk = C.c_int(), C.c_int()
+        _lib.check(ctx.lib.calz_project_and_normalize(ctx.h, hi - lo, 1, qb, lds, mc, s, C.c_void_p(Xd.data_ptr()), ld, 1,
+                                                      _lib.QR[args.backend], C.c_void_p(Zd.data_ptr()), ld, rp,
+                                                      Rl.ctypes.data_as(_lib.c_dp), C.byref(sec), C.byref(rk)), ctx.h)
+        ctx.sync()
+        QZ = Zd[:, : hi - lo].T.cpu().numpy()
+        blk_err = max(blk_err, float(np.max(np.linalg.norm(QZ - Qo[lo:hi, (k - 1) * s + 1:k * s + 1], axis=0))))
+    check("per-block basis vectors 1e-10", blk_err < 1e-10, "%.3e" % blk_err)
     # MPK alone, through the host flavour with the communicator (owned rows in, owned rows out)
     v = r / np.sqrt(r @ r)
     V = api.matrix_powers_newton(dm, v[lo:hi], s, shifts, 1)
     Vo = kernels.matrix_powers_newton(A, v, s, shifts, 1)
+    Vp = partition.mpk_partitioned(A, v, s, shifts, world, "newton", halo_level=L)
+    check("P-way oracle MPK == 1-way", np.max(np.abs(Vp - Vo)) <= 1e-13 * np.max(np.abs(Vo)))
     e = np.max(np.linalg.norm(V - Vo[lo:hi], axis=0) / np.linalg.norm(Vo[lo:hi], axis=0))
     check("mpk owned rows 1e-13", e < 1e-13, "%.3e" % e)
     # identical small results on every rank (deterministic reductions)
@@ -120,7 +159,8 @@ def main():
     if rank == 0:
         flat = [f for fs in allf for f in fs]
         print("dist_check P=%d %s n=%d s=%d backend=%s layout=%s: %s" % (world, args.matrix, n, s, args.backend, dm.layout, "OK" if not flat else "FAILED"))
-        print("  max |T-To|/max|To| = %.2e, Q rows err %.2e, mpk err %.2e, ghosts %d" % (np.abs(T - To).max() / sc, err, e, ghosts.size))
+        print("  max |T-To|/max|To| = %.2e, Q trajectory err %.2e, per-block Q err %.2e, mpk err %.2e, ghosts %d, halo level %d" %
+              (np.abs(T - To).max() / sc, err, blk_err, e, ghosts.size, L))
         for f in flat:
             print("  " + f)
     dist.destroy_process_group()

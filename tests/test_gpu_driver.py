@@ -258,8 +258,6 @@ def test_full_size_c3_block_properties():
     dm.close()
 
 
-@pytest.mark.skipif(os.environ.get("CALZ_TEST_EXPERIMENTAL", "0") != "1", reason="device adapter of the restarted driver not yet run on "
-                    "hardware (its control flow is covered on the CPU by tests/test_restart_host.py): CALZ_TEST_EXPERIMENTAL=1 enables it")
 @pytest.mark.parametrize("orth", ["local", "full"])
 def test_device_resident_restarted_ca_lanczos(orth):
     # test_restart_diagonal_matrices.m:8-36 scaled down; Q, Q_conv and the restart vector never leave the GPU

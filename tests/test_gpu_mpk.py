@@ -40,6 +40,46 @@ MATS = {
 }
 
 
+def _arrow(n=9000):
+    """hub rows far beyond the long-row threshold (2048 entries): the first two rows/columns are full"""
+    i = np.arange(n)
+    T = sp.diags([-np.ones(n - 1), 4.0 + 0.001 * i, -np.ones(n - 1)], [-1, 0, 1]).tolil()
+    T[0, :] = np.cos(0.01 * i) * 0.01; T[:, 0] = (np.cos(0.01 * i) * 0.01).reshape(-1, 1)
+    T[1, 2:] = -0.002; T[2:, 1] = -0.002
+    T[0, 0] = 50.0
+    A = T.tocsr(); A.sort_indices()
+    return A
+
+
+@pytest.mark.parametrize("layout", ["csr", "sell"])
+def test_long_rows_take_the_segmented_kernel(layout):
+    A = _arrow()
+    n = A.shape[0]
+    dm = api.DeviceMatrix(A, s_max=4, layout=layout)
+    assert dm.info("n_long_rows") == 2
+    assert dm.info("nnz_loc") == A.nnz
+    q = np.cos(0.1 * np.arange(n)) + 1.5
+    y = A @ q
+    np.testing.assert_allclose(api.SpMV(dm, q), y, rtol=0, atol=1e-13 * np.linalg.norm(y, np.inf))
+    lam = np.array([40.0, 3.0, 20.0, 8.0])
+    V = api.matrix_powers_newton(dm, q / np.linalg.norm(q), 4, lam, 1)
+    Vo = kernels.matrix_powers_newton(A, q / np.linalg.norm(q), 4, lam, 1)
+    assert relcols(V, Vo) < 1e-12
+    dm.close()
+
+
+def test_powerlaw_rows_generator_matches_whole_matrix():
+    """the per-rank generator of the C4 matrix: any row slice equals the same rows of the whole matrix, symmetric, SPD by dominance"""
+    n = 4000
+    A = gallery.powerlaw_spd_rows(n, 10.0, seed=3)
+    assert abs(A - A.T).max() == 0
+    d = A.diagonal()
+    assert np.all(d - (abs(A).sum(axis=1).A1 - d) >= 1.0 - 1e-12)
+    for lo, hi in ((0, 500), (1234, 3000), (3000, 4000)):
+        S = gallery.powerlaw_spd_rows(n, 10.0, seed=3, row_lo=lo, row_hi=hi)
+        assert abs(S - A[lo:hi]).max() == 0
+
+
 @pytest.mark.parametrize("layout", ["csr", "sell"])
 @pytest.mark.parametrize("name", list(MATS))
 def test_spmv_and_monomial(name, layout):

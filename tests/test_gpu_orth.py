@@ -233,3 +233,29 @@ def test_full_size_orth_properties():
     assert rel(Rt, Rc) < 1e-9
     assert orth(Qt) < 1e-13 and orth(Qc) < 1e-9
     assert rel(Qt @ Rt, X) < 1e-13 and rel(Qc @ Rc, X) < 1e-13
+
+
+@pytest.mark.parametrize("cols", [(9,), (9, 8), (5, 17, 8), (40, 8), (3, 9, 8, 8, 8)])
+def test_orth_error_entry_point(cols):
+    """calz_orth_error: compute_orth_err (ca_lanczos.m:99-107) and ||I - Q'Q||_F (restarted_ca_lanczos.m:165-168) on the device"""
+    import torch
+    from ca_lanczos_b200 import solver
+    n, s = 20011, 8
+    tot = sum(cols)
+    X = gallery.tall_skinny(n, tot, seed=5) * (2.0 ** np.arange(tot))[None, :]
+    Q = np.linalg.qr(X)[0]
+    Q = Q + 1e-9 * gallery.tall_skinny(n, tot, seed=6)            # a basis that has lost some orthogonality
+    ctx = api.default_context()
+    ld = (n + 31) // 32 * 32
+    dev = torch.device("cuda", ctx.device)
+    blocks, keep, c0 = [], [], 0
+    for c in cols:
+        t = torch.zeros((c, ld), dtype=torch.float64, device=dev)
+        t[:, :n] = torch.as_tensor(np.ascontiguousarray(Q[:, c0:c0 + c].T), device=dev)
+        keep.append(t); blocks.append((t.data_ptr(), ld, c)); c0 += c
+    torch.cuda.synchronize(dev)
+    G = Q.T @ Q
+    fro = np.linalg.norm(np.eye(tot) - G, "fro")
+    last = np.abs(G[: tot - s - 1, tot - s - 1:]).max() if tot > s + 1 else np.abs(G - np.eye(tot)).max()
+    assert solver.orth_error(ctx, n, blocks, "fro") == pytest.approx(fro, rel=1e-6)
+    assert solver.orth_error(ctx, n, blocks, "lastblock", s) == pytest.approx(last, rel=1e-6)
