@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libcalz.so")
-SOURCES = ["ctx.cu", "matrix.cu", "mpk.cu", "mpk_ufast.cu", "tsops.cu", "tiles.cu", "tsqr.cu", "orth.cu", "p2p.cu"]
+SOURCES = ["ctx.cu", "matrix.cu", "mpk.cu", "tsops.cu", "tiles.cu", "tsqr.cu", "orth.cu", "p2p.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr",

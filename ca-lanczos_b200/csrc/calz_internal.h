@@ -86,7 +86,6 @@ struct calz_ctx {
                                      // (measured at C3: 1.45 ms per MPK vs 1.19 ms for the L1-gather kernel => opt-in)
     int64_t opt_pan_fused_solve = 1; // tile pipeline, Cholesky back ends: downdated Gram + fused (update, triangular solve) last pass
     int64_t opt_mpk_dict_mode = -1;  // dictionary SELL: where the dictionary lives (0 shared memory, 2 constant bank, -1 by code uniformity)
-    int64_t opt_mpk_uniform_fast = 0;  // EXPERIMENTAL: cached-code-word fast path of the dictionary SpMV (k_spmv_selld_ufast)
     int64_t opt_mpk_halo_level = 0;  // depth of the ghost closure = MPK steps per halo exchange (0: automatic, see matrix.cu)
     int64_t opt_mpk_persist = 1;     // dictionary SELL: persistent, software-pipelined kernel (0 = one CTA per 16 slices)
     int64_t opt_sell_dict = 1;       // layout=auto may pick the dictionary-coded SELL variant
@@ -100,6 +99,8 @@ struct calz_ctx {
     calz::DevBuf small;              // small device matrices (C, G, R, flags)
     calz::DevBuf work[4];            // n x c work blocks (Y, Z, host-flavour staging ...)
     calz::DevBuf tsqr_r;             // TSQR leaf R factors / tree
+    void* tsqr_plan = nullptr;       // tsqr.cu: the live factorisation (levels, reflector storage); freed by tsqr_plan_free
+    void* pan_ring = nullptr;        // orth.cu: ring of in-flight projectAndNormalize calls; freed by pan_ring_free
     unsigned int* ticket = nullptr;  // "last CTA" tickets
     double* pinned = nullptr;        // pinned host staging for small results
     size_t pinned_bytes = 0;
@@ -151,6 +152,9 @@ void p2p_teardown(calz_ctx* ctx);
 bool p2p_allreduce_ok(const calz_ctx* ctx, size_t count);
 int p2p_allreduce(calz_ctx* ctx, double* dev, size_t count);
 int p2p_check(calz_ctx* ctx);
+
+void tsqr_plan_free(calz_ctx* ctx);      // tsqr.cu
+void pan_ring_free(calz_ctx* ctx);       // orth.cu
 
 // host small algebra (smallalg.cu)
 void svd_singular_values(int c, const double* R, int ldR, double* sigma);   // one-sided Jacobi

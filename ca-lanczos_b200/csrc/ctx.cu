@@ -186,6 +186,8 @@ int calz_finalize(calz_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     p2p_teardown(ctx);
+    tsqr_plan_free(ctx);
+    pan_ring_free(ctx);
     if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
     DevBuf* bufs[] = {&ctx->partials, &ctx->small, &ctx->work[0], &ctx->work[1], &ctx->work[2], &ctx->work[3], &ctx->tsqr_r};
     for (DevBuf* b : bufs)
@@ -238,7 +240,6 @@ int calz_set_option(calz_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "pan_fused_solve")) ctx->opt_pan_fused_solve = value;
     else if (!strcmp(key, "mpk_persist")) ctx->opt_mpk_persist = value;
     else if (!strcmp(key, "mpk_halo_level")) ctx->opt_mpk_halo_level = value;
-    else if (!strcmp(key, "mpk_uniform_fast")) ctx->opt_mpk_uniform_fast = value;
     else if (!strcmp(key, "mpk_dict_mode")) ctx->opt_mpk_dict_mode = value;
     else if (!strcmp(key, "mpk_xs_rows")) ctx->opt_mpk_xs_rows = value;
     else if (!strcmp(key, "tile_pipeline")) ctx->opt_tile_pipeline = value;

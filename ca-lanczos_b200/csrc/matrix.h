@@ -79,8 +79,6 @@ struct calz_mat {
 };
 
 namespace calz {
-int launch_selld_ufast(calz_mat* m, const double* x, const double* xp, double* y, int64_t s0, int64_t s1, bool newton, double shift,
-                       double pair);                                   // mpk_ufast.cu (experimental, opt-in)
 int p2p_halo_setup(calz_mat* m);
 void p2p_halo_teardown(calz_mat* m);
 int p2p_halo_exchange(calz_mat* m, double* w, int col);

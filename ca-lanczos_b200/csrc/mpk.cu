@@ -421,8 +421,6 @@ int launch_selld(calz_mat* m, const double* x, const double* xp, double* y, int6
     if (dm < 0) dm = m->dict_uniform >= 0.75 ? DM_CONST : DM_SHARED;
     const int key = (newton ? 1 : 0) | (ctx->opt_mpk_persist ? 2 : 0) | (dm << 2);
     if (!newton) { shift = 0.0; pair = 0.0; }
-    if (ctx->opt_mpk_uniform_fast && ctx->opt_mpk_persist && dm == DM_CONST)      // experimental kernel, mpk_ufast.cu
-        return launch_selld_ufast(m, x, xp, y, s0, s1, newton, shift, pair);
 #define CALZ_SELLD_CASE(NW, PS, DM) \
     case ((NW) | ((PS) << 1) | ((DM) << 2)): return launch_selld_t<NW != 0, PS != 0, DM>(m, x, xp, y, s0, s1, shift, pair);
     switch (key) {

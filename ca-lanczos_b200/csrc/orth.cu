@@ -295,7 +295,6 @@ struct PanSlot {
 };
 constexpr int kPanSlots = 8;
 struct PanRing { PanSlot slot[kPanSlots]; int next = 0; };
-static std::map<calz_ctx*, PanRing*> g_rings;
 
 static int pan_enqueue(calz_ctx* ctx, int64_t n, int nblk, const double* const* Qblk, const int64_t* ldQ,
                        const int* mcols, int c, const double* X, int64_t ldX, int doreorth, int backend,
@@ -483,10 +482,9 @@ static int pan_finish(calz_ctx* ctx, PanSlot& slot, double* const* Rblk, double*
     return CALZ_OK;
 }
 
-static PanRing* ring_of(calz_ctx* ctx) {
-    PanRing*& r = g_rings[ctx];
-    if (!r) r = new PanRing();
-    return r;
+static PanRing* ring_of(calz_ctx* ctx) {      // lives in the context (freed by calz_finalize through pan_ring_free)
+    if (!ctx->pan_ring) ctx->pan_ring = new PanRing();
+    return (PanRing*)ctx->pan_ring;
 }
 
 int calz_project_and_normalize(calz_ctx* ctx, int64_t n, int nblk, const double* const* Qblk, const int64_t* ldQ,
@@ -515,6 +513,23 @@ int calz_pan_collect(calz_ctx* ctx, int ticket, double* const* Rblk, double* Rla
     if (!ctx || ticket < 0 || ticket >= kPanSlots) return set_error(ctx, CALZ_ERR_BADARG, "calz_pan_collect: bad ticket");
     return pan_finish(ctx, ring_of(ctx)->slot[ticket], Rblk, Rlast, second_pass, rank, false, needs_refine);
 }
+
+}  // extern "C"
+
+namespace calz {
+void pan_ring_free(calz_ctx* ctx) {
+    PanRing* r = (PanRing*)ctx->pan_ring;
+    if (!r) return;
+    for (PanSlot& s : r->slot) {
+        if (s.ev) cudaEventDestroy(s.ev);
+        if (s.host) cudaFreeHost(s.host);
+    }
+    delete r;
+    ctx->pan_ring = nullptr;
+}
+}  // namespace calz
+
+extern "C" {
 
 // ------------------------------------------------------------------------------------------ host flavours
 namespace {

@@ -172,3 +172,30 @@ def tall_skinny(n: int, c: int, seed: int = 0, row0: int = 0) -> np.ndarray:
     u = (bits >> np.uint64(11)).astype(np.float64) * (1.0 / (1 << 53))
     X = (2.0 * u - 1.0) * (2.0 ** -np.arange(c, dtype=np.float64))[None, :]
     return np.asfortranarray(X)
+
+
+def tall_skinny_device(n, c, dev, ld, row0=0, seed=0):
+    """``tall_skinny`` generated ON the device with torch integer ops (same counter-based generator, bit-identical; C5 at
+    n = 1e8 would take minutes and 13.6 GB of PCIe from the host): a (c, ld) row-major tensor == n x c column-major, ld >= n."""
+    import torch
+    X = torch.zeros((c, ld), dtype=torch.float64, device=dev)
+    M64 = (1 << 64) - 1
+
+    def s64(v):      # python int (mod 2^64) -> signed int64 value
+        v &= M64
+        return v - (1 << 64) if v >= (1 << 63) else v
+
+    def lsr(z, k):   # logical shift right on int64 tensors
+        return (z >> k) & ((1 << (64 - k)) - 1)
+    chunk = 1 << 24
+    for j in range(c):
+        for r0 in range(0, n, chunk):
+            m = min(chunk, n - r0)
+            i = torch.arange(row0 + r0, row0 + r0 + m, dtype=torch.int64, device=dev)
+            z = i * c + j + s64(seed * 0xD1B54A32D192ED03) + s64(0x9E3779B97F4A7C15)
+            z = (z ^ lsr(z, 30)) * s64(0xBF58476D1CE4E5B9)
+            z = (z ^ lsr(z, 27)) * s64(0x94D049BB133111EB)
+            z = z ^ lsr(z, 31)
+            u = lsr(z, 11).to(torch.float64) * (1.0 / (1 << 53))
+            X[j, r0:r0 + m] = (2.0 * u - 1.0) * (2.0 ** -j)
+    return X

@@ -285,25 +285,3 @@ def test_full_size_c2_basis_identity():
     d = np.linspace(1, 100, n)                                    # diagonal A: closed form prod(d - lam_i) * v
     exact = np.prod(d[:, None] - lam[None, :], axis=1) * v        # rows with d ~ lam_i cancel: compare norm-wise
     assert np.linalg.norm(V[:, s] - exact) <= 1e-12 * np.linalg.norm(exact)
-
-
-@pytest.mark.skipif(os.environ.get("CALZ_TEST_EXPERIMENTAL", "0") != "1", reason="experimental kernel, not yet measured on hardware: "
-                    "CALZ_TEST_EXPERIMENTAL=1 enables the check")
-@pytest.mark.parametrize("name", ["lap3d", "poisson100", "ragged"])
-def test_experimental_cached_code_word_kernel_is_bit_identical(name):
-    A = _few_values_ragged() if name == "ragged" else MATS[name]()
-    n = A.shape[0]
-    v = np.cos(0.11 * np.arange(n)) + 0.3
-    lam = np.array([5.0, 0.5, 3.0, 1.0])
-    ctx = api.default_context()
-    dm = api.DeviceMatrix(A, 4, "selld")
-    ref = (api.matrix_powers_newton(dm, v, 4, lam, 1), api.matrix_powers_monomial(dm, v, 3))
-    ctx.set_option("mpk_dict_mode", 2)
-    ctx.set_option("mpk_uniform_fast", 1)
-    try:
-        np.testing.assert_array_equal(api.matrix_powers_newton(dm, v, 4, lam, 1), ref[0])
-        np.testing.assert_array_equal(api.matrix_powers_monomial(dm, v, 3), ref[1])
-    finally:
-        ctx.set_option("mpk_uniform_fast", 0)
-        ctx.set_option("mpk_dict_mode", -1)
-        dm.close()
