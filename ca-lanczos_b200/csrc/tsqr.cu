@@ -25,7 +25,7 @@ namespace calz {
 
 namespace {
 
-constexpr int kTsqrThreads = 256;
+constexpr int kTsqrThreads = 128;                // 4 warps per leaf; RPL rows per thread (RPL*CW <= 64 doubles of the leaf per thread)
 constexpr int kTsqrWarps = kTsqrThreads / 32;
 
 // compile-time loop: f(std::integral_constant<int, I>) for I = B .. E-1
@@ -63,8 +63,7 @@ __device__ __forceinline__ void warp_reduce_scatter(double (&p)[KP], int lane) {
     }
 }
 
-// CTA-wide sums of K <= KP values: every thread contributes p[0..KP) and afterwards reads total k from red[w][k], w = 0..7
-// (summed in warp order by the caller).  `red` is this column's exchange buffer: [kTsqrWarps][KP] doubles.
+// every thread contributes p[0..KP); afterwards red[w*KP + k], w = 0..3, are the per-warp totals of value k
 template <int KP>
 __device__ __forceinline__ void cta_reduce_post(double (&p)[KP], double* red, int lane, int warp) {
     warp_reduce_scatter<KP>(p, lane);
@@ -79,16 +78,25 @@ __device__ __forceinline__ double cta_reduce_get(const double* red, int KP, int 
 }
 
 // ---------------------------------------------------------------------------------------------------------------- factor
-// One leaf per CTA: local row lr = i*256 + tid (i < RPL).  Column j: pivot = local row j (thread j, i = 0).
+// One leaf per CTA: local row lr = i*128 + tid (i < RPL).  Column j: pivot = local row j (thread j, i = 0).  Per column ONE batched
+// reduction of CW values over this thread's rows BELOW the pivot:
+//     sum x^2 | sum x*a_l for the trailing columns l > j | sum x*v_i for the finished reflectors i < j
+// -> butterfly -> shared memory; barrier; warp 0 finishes the sums, runs dlarfg ONCE (sqrt and the two reciprocals are ~100
+// instructions in fp64: not worth repeating in 128 threads), posts {beta, tau, scale} and per trailing column {w_l, w_l*scale}, and
+// keeps v_i'v_j (the compact-WY data the top-down sweep needs, see k_tsqr_apply); barrier; every thread scales its part of the
+// reflector and updates its rows.
 template <int CW, int RPL>
 __global__ void __launch_bounds__(kTsqrThreads, 2)
 k_tsqr_leaf(long long nrows, int c, const double* A, long long ldA, double* V, long long ldV, double* __restrict__ tau_out,
-            double* __restrict__ Rstack, long long ldR, const int* __restrict__ pred, int want) {
+            double* __restrict__ Rstack, long long ldR, double* __restrict__ Gout, const int* __restrict__ pred, int want) {
     if (pred && *pred != want) return;
     constexpr int LEAF = kTsqrThreads * RPL;
-    constexpr int KPMAX = pow2_ceil(CW);
-    __shared__ double red[2][kTsqrWarps * KPMAX];
-    __shared__ double piv[2][CW];
+    constexpr int KP = pow2_ceil(CW);
+    __shared__ double red[kTsqrWarps * KP];
+    __shared__ double piv[CW];                        // the pivot row: columns j.. at [0, K), columns 0..j-1 at [K, CW)
+    __shared__ __align__(16) double coef[2 * CW];     // {w_l, w_l*scale} per trailing column
+    __shared__ double hdr[4];                         // beta, tau, scale
+    __shared__ double Gs[CW * CW];                    // strict upper triangle of V'V
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long r0 = (long long)blockIdx.x * LEAF;
 
@@ -99,66 +107,78 @@ k_tsqr_leaf(long long nrows, int c, const double* A, long long ldA, double* V, l
 #pragma unroll
         for (int j = 0; j < CW; ++j) a[i][j] = (row < nrows && j < c) ? A[row + (long long)j * ldA] : 0.0;
     }
+    for (int e = tid; e < CW * CW; e += kTsqrThreads) Gs[e] = 0.0;
     double my_tau = 0.0;                              // thread j keeps tau_j
 
     static_for<0, CW>([&](auto jc) {
         constexpr int j = decltype(jc)::value;
         if (j < c) {
-            constexpr int K = CW - j, KP = pow2_ceil(K);
-            double* rb = red[j & 1];
-            double* pb = piv[j & 1];
-            // partial sums over this thread's rows BELOW the pivot: p[0] -> sum x^2, p[k] -> sum x*a(:,j+k)
+            constexpr int K = CW - j;
+            // value k < K: column j + k ; value K + i: finished reflector i < j
             double p[KP];
 #pragma unroll
             for (int k = 0; k < KP; ++k) p[k] = 0.0;
+            double x[RPL];
 #pragma unroll
             for (int i = 0; i < RPL; ++i) {
-                const bool below = (i > 0) || (tid > j);
-                const double x = below ? a[i][j] : 0.0;
+                x[i] = (i > 0 || tid > j) ? a[i][j] : 0.0;
 #pragma unroll
-                for (int k = 0; k < K; ++k) p[k] = fma(x, a[i][j + k], p[k]);
+                for (int k = 0; k < K; ++k) p[k] = fma(x[i], a[i][j + k], p[k]);
+#pragma unroll
+                for (int q = 0; q < j; ++q) p[K + q] = fma(x[i], a[i][q], p[K + q]);
             }
-            cta_reduce_post<KP>(p, rb, lane, warp);
+            cta_reduce_post<KP>(p, red, lane, warp);
             if (tid == j) {                           // the pivot row travels through shared memory as well
 #pragma unroll
-                for (int k = 0; k < K; ++k) pb[k] = a[0][j + k];
+                for (int k = 0; k < K; ++k) piv[k] = a[0][j + k];
+#pragma unroll
+                for (int q = 0; q < j; ++q) piv[K + q] = a[0][q];
             }
             __syncthreads();
-            // dlarfg on column j (every thread, redundantly, from identical inputs)
-            const double ss = cta_reduce_get(rb, KP, 0);
-            const double alpha = pb[0];
-            double tj = 0.0, scale = 0.0, beta = alpha;
-            if (ss != 0.0) {
-                beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
-                tj = (beta - alpha) / beta;
-                scale = 1.0 / (alpha - beta);
+            if (warp == 0) {
+                // dlarfg on column j, then w_l = tau * v'a_l = tau * (pivot entry + scale * sum_below x*a_l)
+                const double S = (lane < CW) ? cta_reduce_get(red, KP, lane) : 0.0;
+                const double ss = __shfl_sync(0xffffffffu, S, 0);
+                const double alpha = piv[0];
+                double tj = 0.0, scale = 0.0, beta = alpha;
+                if (ss != 0.0) {
+                    beta = -copysign(sqrt(fma(alpha, alpha, ss)), alpha);
+                    tj = (beta - alpha) / beta;
+                    scale = 1.0 / (alpha - beta);
+                }
+                if (lane >= 1 && lane < K) {
+                    const double w = tj * fma(scale, S, piv[lane]);
+                    coef[2 * lane] = w;
+                    coef[2 * lane + 1] = w * scale;
+                }
+                if (lane >= K && lane < CW) Gs[(lane - K) * CW + j] = fma(scale, S, piv[lane]);      // v_i'v_j, i = lane - K
+                if (lane == 0) { hdr[0] = beta; hdr[1] = tj; hdr[2] = scale; }
             }
+            __syncthreads();
+            const double beta = hdr[0], tj = hdr[1], scale = hdr[2];
             if (tid == j) my_tau = tj;
-            // v: 1 at the pivot, x*scale below, 0 above
-            double v[RPL];
+            // v: 1 at the pivot (beta is stored there), x*scale below; rows above keep their R entries
 #pragma unroll
             for (int i = 0; i < RPL; ++i) {
-                const bool below = (i > 0) || (tid > j);
-                const bool pivot = (i == 0) && (tid == j);
-                v[i] = below ? a[i][j] * scale : (pivot ? 1.0 : 0.0);
-                if (below) a[i][j] = v[i];
-                if (pivot) a[i][j] = beta;
+                if (i > 0 || tid > j) a[i][j] = x[i] * scale;
+                else if (tid == j) a[i][j] = beta;
             }
             if (tj != 0.0) {
 #pragma unroll
                 for (int k = 1; k < K; ++k) {
                     if (j + k < c) {
-                        // w = tau * v'a_l = tau * (pivot entry + scale * sum_below x*a_l)
-                        const double w = tj * fma(scale, cta_reduce_get(rb, KP, k), pb[k]);
+                        const double2 wc = *reinterpret_cast<const double2*>(&coef[2 * k]);
+                        // below rows: a_l -= (w*scale) * x ; pivot row: a_l -= w   (x is 0 on the pivot row and above it)
 #pragma unroll
-                        for (int i = 0; i < RPL; ++i) a[i][j + k] = fma(-w, v[i], a[i][j + k]);
+                        for (int i = 0; i < RPL; ++i) a[i][j + k] = fma(-wc.y, x[i], a[i][j + k]);
+                        if (tid == j) a[0][j + k] -= wc.x;
                     }
                 }
             }
         }
     });
 
-    // reflectors (+R above them) back to V, R to the stack of the next level, tau
+    // reflectors (+R above them) back to V, R to the stack of the next level, tau, V'V
 #pragma unroll
     for (int i = 0; i < RPL; ++i) {
         const long long row = r0 + i * kTsqrThreads + tid;
@@ -172,76 +192,115 @@ k_tsqr_leaf(long long nrows, int c, const double* A, long long ldA, double* V, l
             if (j < c) Rstack[(long long)blockIdx.x * c + tid + (long long)j * ldR] = (j >= tid) ? a[0][j] : 0.0;
         tau_out[(long long)blockIdx.x * c + tid] = my_tau;
     }
+    __syncthreads();
+    for (int e = tid; e < c * c; e += kTsqrThreads) Gout[(long long)blockIdx.x * c * c + e] = Gs[(e / c) * CW + (e % c)];     // row-major c x c
 }
 
 // ---------------------------------------------------------------------------------------------------------------- apply
-// B = H_1 ... H_c [W_leaf; 0]  for every leaf (W_leaf = rows leaf*c.. of W), written to Out (may alias V).
-template <int CW, int RPL>
-__global__ void __launch_bounds__(kTsqrThreads, 2)
-k_tsqr_apply(long long nrows, int c, const double* V, long long ldV, const double* __restrict__ tau_in,
+// Q_leaf = H_1 ... H_c [W_leaf; 0] for every leaf, in compact-WY form: H_1...H_c = I - V T V' with T^-1 = striu(V'V) + diag(1/tau),
+// and since only the top c rows of [W;0] are non-zero,
+//     Q_leaf = [W;0] - V * M,   M = T * (Vtop' * W)           (Vtop = the unit lower triangular top c x c block of V).
+// striu(V'V) comes from the factorisation (no reduction here at all): a c x c triangular solve per leaf in the prologue, then
+// a streaming update, RC rows per thread at a time.  A reflector with tau = 0 is the identity: its column of V is ignored.
+template <int CW, int RPL, int RC>
+__global__ void __launch_bounds__(kTsqrThreads, (CW <= 16 ? 4 : 3))
+k_tsqr_apply(long long nrows, int c, const double* V, long long ldV, const double* __restrict__ tau_in, const double* __restrict__ G,
              const double* __restrict__ W, long long ldW, double* Out, long long ldOut) {
+    static_assert(RPL % RC == 0, "row chunks");
     constexpr int LEAF = kTsqrThreads * RPL;
-    constexpr int KP = pow2_ceil(CW);
-    __shared__ double red[2][kTsqrWarps * KP];
+    __shared__ double U[CW][CW + 1];                  // striu(V'V)
+    __shared__ double Vt[CW][CW + 1];                 // Vtop
+    __shared__ double Ws[CW][CW + 1];
+    __shared__ __align__(16) double Ms[CW][CW];
     __shared__ double taus[CW];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const long long r0 = (long long)blockIdx.x * LEAF;
-    if (tid < CW) taus[tid] = tid < c ? tau_in[(long long)blockIdx.x * c + tid] : 0.0;
 
-    double b[RPL][CW];
+    auto load_chunk = [&](int ch, double (&v)[RC][CW]) {
 #pragma unroll
-    for (int i = 0; i < RPL; ++i)
+        for (int i = 0; i < RC; ++i) {
+            const long long row = r0 + (long long)(ch * RC + i) * kTsqrThreads + tid;
 #pragma unroll
-        for (int j = 0; j < CW; ++j)
-            b[i][j] = (i == 0 && tid < c && j < c) ? W[(long long)blockIdx.x * c + tid + (long long)j * ldW] : 0.0;
-
-    auto load_v = [&](int j, double (&v)[RPL]) {     // reflector j: 1 at local row j, stored tail below, 0 above
-#pragma unroll
-        for (int i = 0; i < RPL; ++i) {
-            const long long row = r0 + i * kTsqrThreads + tid;
-            const int lrow = i * kTsqrThreads + tid;
-            const double x = (row < nrows && j >= 0 && j < c) ? V[row + (long long)j * ldV] : 0.0;
-            v[i] = (lrow > j) ? x : (lrow == j ? 1.0 : 0.0);
+            for (int j = 0; j < CW; ++j) v[i][j] = (row < nrows && j < c) ? V[row + (long long)j * ldV] : 0.0;
         }
     };
-    double vn[RPL];
-    load_v(c - 1, vn);
+    double v[RC][CW];
+    load_chunk(0, v);                                 // in flight behind the prologue
+    if (tid < CW) taus[tid] = tid < c ? tau_in[(long long)blockIdx.x * c + tid] : 0.0;
+    for (int e = tid; e < CW * CW; e += kTsqrThreads) {
+        const int r = e % CW, l = e / CW;
+        const bool in = r < c && l < c;
+        Ws[r][l] = in ? W[(long long)blockIdx.x * c + r + (long long)l * ldW] : 0.0;
+        U[l][r] = in ? G[(long long)blockIdx.x * c * c + (long long)l * c + r] : 0.0;          // U[i][j] = G(i,j), row-major in G
+        // Vtop(r, l): 1 on the diagonal, the stored tail below it
+        const long long row = r0 + r;
+        Vt[r][l] = (r > l && in && row < nrows) ? V[row + (long long)l * ldV] : (r == l ? 1.0 : 0.0);
+    }
     __syncthreads();
-    int buf = 0;                                      // exchange buffers alternate per EXECUTED reduction (one barrier each)
-    for (int j = c - 1; j >= 0; --j) {
-        double v[RPL];
+    if (tid < CW) {
+        // column l = tid of  Y = Vtop' * W  and of  M = T * Y  (back substitution with T^-1 = U + diag(1/tau))
+        const int l = tid;
+        double m[CW];
 #pragma unroll
-        for (int i = 0; i < RPL; ++i) v[i] = vn[i];
-        load_v(j - 1, vn);                            // prefetch the next reflector behind this one's reduction
-        const double tj = taus[j];
-        if (tj != 0.0) {                              // uniform over the CTA
-            double* rb = red[buf];
-            buf ^= 1;
-            double p[KP];
+        for (int i = 0; i < CW; ++i) {
+            double y = 0.0;
 #pragma unroll
-            for (int k = 0; k < KP; ++k) p[k] = 0.0;
+            for (int r = 0; r < CW; ++r)
+                if (r >= i) y = fma(Vt[r][i], Ws[r][l], y);
+            m[i] = y;
+        }
 #pragma unroll
-            for (int i = 0; i < RPL; ++i)
+        for (int ii = 0; ii < CW; ++ii) {
+            const int i = CW - 1 - ii;
+            double acc = m[i];
 #pragma unroll
-                for (int k = 0; k < CW; ++k) p[k] = fma(v[i], b[i][k], p[k]);
-            cta_reduce_post<KP>(p, rb, lane, warp);
-            __syncthreads();
+            for (int k = 0; k < CW; ++k)
+                if (k > i) acc = fma(-U[i][k], m[k], acc);
+            m[i] = acc * taus[i];                     // tau = 0: the row is zero (identity reflector)
+        }
 #pragma unroll
-            for (int k = 0; k < CW; ++k) {
-                if (k < c) {
-                    const double w = tj * cta_reduce_get(rb, KP, k);
+        for (int i = 0; i < CW; ++i) Ms[i][l] = m[i];
+    }
+    __syncthreads();
+    // Q rows = [W;0] - V*M
 #pragma unroll
-                    for (int i = 0; i < RPL; ++i) b[i][k] = fma(-w, v[i], b[i][k]);
+    for (int ch = 0; ch < RPL / RC; ++ch) {
+        if (ch > 0) load_chunk(ch, v);
+        if (ch == 0 && tid < c) {                     // the top c rows: unit diagonal, nothing above it
+#pragma unroll
+            for (int j = 0; j < CW; ++j) v[0][j] = Vt[tid][j];
+        }
+#pragma unroll
+        for (int l0 = 0; l0 < CW; l0 += 4) {
+            if (l0 < c) {
+                double b[RC][4];
+#pragma unroll
+                for (int i = 0; i < RC; ++i)
+#pragma unroll
+                    for (int l = 0; l < 4; ++l) b[i][l] = (ch == 0 && i == 0 && tid < c) ? Ws[tid < CW ? tid : 0][l0 + l] : 0.0;
+#pragma unroll
+                for (int j = 0; j < CW; ++j) {
+                    if (j < c) {
+                        const double2 m0 = *reinterpret_cast<const double2*>(&Ms[j][l0]);
+                        const double2 m1 = *reinterpret_cast<const double2*>(&Ms[j][l0 + 2]);
+#pragma unroll
+                        for (int i = 0; i < RC; ++i) {
+                            b[i][0] = fma(-v[i][j], m0.x, b[i][0]);
+                            b[i][1] = fma(-v[i][j], m0.y, b[i][1]);
+                            b[i][2] = fma(-v[i][j], m1.x, b[i][2]);
+                            b[i][3] = fma(-v[i][j], m1.y, b[i][3]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < RC; ++i) {
+                    const long long row = r0 + (long long)(ch * RC + i) * kTsqrThreads + tid;
+#pragma unroll
+                    for (int l = 0; l < 4; ++l)
+                        if (row < nrows && l0 + l < c) Out[row + (long long)(l0 + l) * ldOut] = b[i][l];
                 }
             }
         }
-    }
-#pragma unroll
-    for (int i = 0; i < RPL; ++i) {
-        const long long row = r0 + i * kTsqrThreads + tid;
-#pragma unroll
-        for (int j = 0; j < CW; ++j)
-            if (row < nrows && j < c) Out[row + (long long)j * ldOut] = b[i][j];
     }
 }
 
@@ -271,7 +330,7 @@ __global__ void k_tsqr_slot(int c, int P, int rank, const double* __restrict__ R
 }
 
 struct Level {
-    double* V; long long ldV; long long nrows; long long leaves; double* tau; double* Rstack; long long ldR;
+    double* V; long long ldV; long long nrows; long long leaves; double* tau; double* Rstack; long long ldR; double* G;
     const double* src; long long ldsrc;      // what the leaf kernel reads (level 0: the caller's matrix; first global level: the staging stack)
 };
 
@@ -283,38 +342,40 @@ struct Plan {
     int first_global = -1;     // index of the first level that works on the gathered stack
 };
 
-int cw_for(int c) { return c <= 8 ? 8 : (c <= 12 ? 12 : (c <= 16 ? 16 : (c <= 24 ? 24 : 32))); }
-int rpl_for(int c) { return c <= 8 ? 4 : (c <= 16 ? 2 : 1); }          // <= 32 doubles of the leaf per thread
+int rpl_for(int c) { return c <= 8 ? 8 : (c <= 16 ? 4 : (c <= 20 ? 3 : 2)); }      // RPL * CW <= 64 doubles of the leaf per thread
 
 template <int CW, int RPL>
 int run_leaf(calz_ctx* ctx, const Level& L, int c, const int* pred, int want) {
     k_tsqr_leaf<CW, RPL><<<(unsigned)L.leaves, kTsqrThreads, 0, ctx->stream>>>(L.nrows, c, L.src, L.ldsrc, L.V, L.ldV, L.tau, L.Rstack,
-                                                                               L.ldR, pred, want);
+                                                                               L.ldR, L.G, pred, want);
     CALZ_LAUNCH_CHECK(ctx);
     return CALZ_OK;
 }
 
 template <int CW, int RPL>
 int run_apply(calz_ctx* ctx, const Level& L, int c, const double* W, long long ldW, double* Out, long long ldOut) {
-    k_tsqr_apply<CW, RPL><<<(unsigned)L.leaves, kTsqrThreads, 0, ctx->stream>>>(L.nrows, c, L.V, L.ldV, L.tau, W, ldW, Out, ldOut);
+    constexpr int RC = CW <= 8 ? 4 : (CW <= 16 ? 2 : 1);
+    k_tsqr_apply<CW, RPL, RC><<<(unsigned)L.leaves, kTsqrThreads, 0, ctx->stream>>>(L.nrows, c, L.V, L.ldV, L.tau, L.G, W, ldW, Out, ldOut);
     CALZ_LAUNCH_CHECK(ctx);
     return CALZ_OK;
 }
 
 int dispatch_leaf(calz_ctx* ctx, const Level& L, int c, const int* pred, int want) {
-    if (c <= 8) return run_leaf<8, 4>(ctx, L, c, pred, want);
-    if (c <= 12) return run_leaf<12, 2>(ctx, L, c, pred, want);
-    if (c <= 16) return run_leaf<16, 2>(ctx, L, c, pred, want);
-    if (c <= 24) return run_leaf<24, 1>(ctx, L, c, pred, want);
-    return run_leaf<32, 1>(ctx, L, c, pred, want);
+    if (c <= 8) return run_leaf<8, 8>(ctx, L, c, pred, want);
+    if (c <= 12) return run_leaf<12, 4>(ctx, L, c, pred, want);
+    if (c <= 16) return run_leaf<16, 4>(ctx, L, c, pred, want);
+    if (c <= 20) return run_leaf<20, 3>(ctx, L, c, pred, want);
+    if (c <= 24) return run_leaf<24, 2>(ctx, L, c, pred, want);
+    return run_leaf<32, 2>(ctx, L, c, pred, want);
 }
 
 int dispatch_apply(calz_ctx* ctx, const Level& L, int c, const double* W, long long ldW, double* Out, long long ldOut) {
-    if (c <= 8) return run_apply<8, 4>(ctx, L, c, W, ldW, Out, ldOut);
-    if (c <= 12) return run_apply<12, 2>(ctx, L, c, W, ldW, Out, ldOut);
-    if (c <= 16) return run_apply<16, 2>(ctx, L, c, W, ldW, Out, ldOut);
-    if (c <= 24) return run_apply<24, 1>(ctx, L, c, W, ldW, Out, ldOut);
-    return run_apply<32, 1>(ctx, L, c, W, ldW, Out, ldOut);
+    if (c <= 8) return run_apply<8, 8>(ctx, L, c, W, ldW, Out, ldOut);
+    if (c <= 12) return run_apply<12, 4>(ctx, L, c, W, ldW, Out, ldOut);
+    if (c <= 16) return run_apply<16, 4>(ctx, L, c, W, ldW, Out, ldOut);
+    if (c <= 20) return run_apply<20, 3>(ctx, L, c, W, ldW, Out, ldOut);
+    if (c <= 24) return run_apply<24, 2>(ctx, L, c, W, ldW, Out, ldOut);
+    return run_apply<32, 2>(ctx, L, c, W, ldW, Out, ldOut);
 }
 
 Plan* plan_of(calz_ctx* ctx) {
@@ -354,7 +415,7 @@ int tsqr_factor(calz_ctx* ctx, int64_t n, int c, const double* A, int64_t ldA, d
     }
     const int nlev = (int)rows.size();
     size_t doubles = 2 * (size_t)c * c;                         // D, spare
-    for (int l = 0; l < nlev; ++l) doubles += (size_t)leaves[l] * c * c + (size_t)leaves[l] * c + 8;
+    for (int l = 0; l < nlev; ++l) doubles += 2 * (size_t)leaves[l] * c * c + (size_t)leaves[l] * c + 8;
     if (P > 1) doubles += 2 * (size_t)P * c * c;                // staging stack (collective buffer) + the global level's reflectors
     const long long ldV0 = round_up(n, 32);
     CALZ_TRY(reserve(ctx, ctx->work[0], (size_t)ldV0 * c * sizeof(double)));
@@ -376,6 +437,7 @@ int tsqr_factor(calz_ctx* ctx, int64_t n, int c, const double* A, int64_t ldA, d
         L.Rstack = p; p += (size_t)leaves[l] * c * c;
         L.ldR = leaves[l] * c;
         L.tau = p; p += (size_t)leaves[l] * c + 8;
+        L.G = p; p += (size_t)leaves[l] * c * c;
     }
     for (int l = 0; l < nlev; ++l) {
         Level& L = plan.levels[l];

@@ -102,9 +102,11 @@ class BlockEngine:
         return Rk.copy()
 
     # ---- ca_lanczos.m:184-223 ('local')
-    def next_block(self, assemble_T: bool = True, events=None, full_reorth: bool = False):
+    def next_block(self, assemble_T: bool = True, events=None, full_reorth: bool = False, extra_blocks=()):
         """``events``: optional ((e0,e1,e2), stream) -- torch CUDA events recorded on libcalz' stream before the MPK,
-        between MPK and projectAndNormalize, and after it (bench.py's per-phase timing)."""
+        between MPK and projectAndNormalize, and after it (bench.py's per-phase timing).
+        ``extra_blocks``: further cells of the projection, (device pointer, ld, columns) each, after {Qprev}: the converged Ritz
+        vectors of the selective driver (ca_lanczos.m:286) -- their coefficient blocks are discarded like in the reference."""
         s = self.s
         self.k += 1
         k = self.k
@@ -115,16 +117,17 @@ class BlockEngine:
         V, ldV = self._mpk(self._qcol((k - 1) * s))
         if events is not None:
             events[0][1].record(events[1])
-        qblk = (C.c_void_p * 1)(self._qcol((k - 2) * s))
-        lds = (C.c_int64 * 1)(self.ld)
-        mc = (C.c_int * 1)(s + 1)
-        rp = (_lib.c_dp * 1)(self._R1.ctypes.data_as(_lib.c_dp))
+        nb = 1 + len(extra_blocks)
+        qblk = (C.c_void_p * nb)(self._qcol((k - 2) * s), *[int(b[0]) for b in extra_blocks])
+        lds = (C.c_int64 * nb)(self.ld, *[int(b[1]) for b in extra_blocks])
+        mc = (C.c_int * nb)(s + 1, *[int(b[2]) for b in extra_blocks])
+        rp = (_lib.c_dp * nb)(self._R1.ctypes.data_as(_lib.c_dp), *[None for _ in extra_blocks])
         second = C.c_int(); rank = C.c_int()
         if full_reorth and self._tmp is None:
             self._tmp = self.torch.zeros((s, self.ld), dtype=self.torch.float64, device=self.Q.device)
             self.torch.cuda.synchronize(self.Q.device)
         dst = self._tmp.data_ptr() if full_reorth else self._qcol((k - 1) * s + 1)
-        check(self.lib.calz_project_and_normalize(self.ctx.h, self.n, 1, qblk, lds, mc, s, C.c_void_p(V + 8 * ldV), ldV,
+        check(self.lib.calz_project_and_normalize(self.ctx.h, self.n, nb, qblk, lds, mc, s, C.c_void_p(V + 8 * ldV), ldV,
                                                   1, _lib.QR[self.backend], C.c_void_p(dst),
                                                   self.ld, rp, self._Rl.ctypes.data_as(_lib.c_dp), C.byref(second),
                                                   C.byref(rank)), self.ctx.h)

@@ -148,12 +148,12 @@ def newton_shifts(dm: DeviceMatrix, q0_ptr, s: int, orth: str = "full"):
 
 # ----------------------------------------------------------------------------------------------- ca_lanczos
 def ca_lanczos(A, r, s, iter, basis="newton", orth="local", backend="cholqr2", ctx: Context | None = None, shifts=None,
-               return_engine=False):
+               return_engine=False, norm_A=None):
     """ca_lanczos.m:24-86 with ca_lanczos_basic (:150-245), device resident.  ``A``: scipy sparse or DeviceMatrix;
     ``r``: host start vector (owned rows).  Returns (T, Q) like the reference (Q as a host array), or the engine."""
     orth = str(orth).lower()
-    if orth not in ("local", "full"):
-        raise NotImplementedError("orth=%s: only 'local' and 'full' are on the hot path" % orth)
+    if orth not in ("local", "full", "periodic", "selective"):
+        raise ValueError("ERROR: Unknown orth type: " + orth)
     if basis.lower() not in ("monomial", "newton"):
         raise ValueError("ERROR: Unknown basis type: " + basis)
     s = int(s)
@@ -173,12 +173,142 @@ def ca_lanczos(A, r, s, iter, basis="newton", orth="local", backend="cholqr2", c
     eng.first_block(None, q_ptr=q_ptr)
     if orth == "local":
         eng.run_blocks(t - 1)
-    else:
+    elif orth == "full":
         for _ in range(t - 1):
             eng.next_block(full_reorth=True)
+    else:
+        _periodic_selective(eng, t, orth, A_host=None if isinstance(A, DeviceMatrix) else A, norm_A=norm_A)
     if return_engine:
         return eng
     return eng.T_matrix(), eng.Q_host()
+
+
+# ----------------------------------------------------------------------------------------------- periodic / selective (N3)
+_EPS = float(np.finfo(np.float64).eps)
+
+
+def update_omega(omega_in, alpha, beta, anorm, s):
+    """ca_lanczos.m:469-539: the omega recurrence (estimated inner products between Lanczos vectors) extended by s rows;
+    ``alpha``/``beta`` = diag(T,0) / diag(T,-1).  Host algebra, O((sk)^2) per block; 1-based work arrays as in the reference."""
+    n = len(alpha)
+    al = np.concatenate([[0.0], np.asarray(alpha, dtype=np.float64)])
+    be = np.concatenate([[0.0], np.asarray(beta, dtype=np.float64)])
+    Tr = _EPS * anorm
+    if omega_in is None or np.size(omega_in) == 0:
+        om = np.zeros((s + 2, s + 2))
+        om[1, 1] = 1.0
+        om[2, 1] = Tr / be[1]; om[2, 2] = 1.0
+        rows = range(2, s + 1)
+    else:
+        m = omega_in.shape[0] - 1
+        om = np.zeros((n + 2, n + 2))
+        om[1:m + 2, 1:m + 2] = omega_in
+        rows = range(m + 1, m + s + 1)
+    for j in rows:
+        binv = 1.0 / be[j]
+        w = be[2] * om[j, 2] + (al[1] - al[j]) * om[j, 1] - be[j] * om[j - 1, 1]
+        om[j + 1, 1] = binv * (w + Tr) if w > 0 else binv * (w - Tr)
+        for k in range(2, j):
+            w = be[k + 1] * om[j, k + 1] + (al[k] - al[j]) * om[j, k] + be[k] * om[j, k - 1] - be[j] * om[j - 1, k]
+            om[j + 1, k] = binv * (w + Tr) if w > 0 else binv * (w - Tr)
+        om[j + 1, j] = binv * Tr
+        om[j + 1, j + 1] = 1.0
+    return om[1:, 1:].copy()
+
+
+def reset_omega(omega_in, anorm, s):
+    """ca_lanczos.m:541-551: after a re-orthogonalisation the last s rows of omega drop back to the round-off level."""
+    Tr = _EPS * anorm
+    m = omega_in.shape[0] - s - 1
+    om = omega_in.copy()
+    for j in range(m + 1, m + s + 1):          # 1-based row j+1 -> 0-based row j
+        om[j, :j] = Tr
+        om[j, j] = 1.0
+    return om
+
+
+def _periodic_selective(eng: BlockEngine, t: int, orth: str, A_host=None, norm_A=None):
+    """ca_lanczos_periodic (ca_lanczos.m:362-467) / ca_lanczos_selective (:248-359) around the device-resident block engine:
+    the omega recurrence / the Ritz convergence test run on the host from T; the re-orthogonalisations
+    (projectAndNormalize against ALL previous vectors, :449; against the converged Ritz vectors, :286), the Ritz vector assembly
+    (:336-337) and normest (:372) run on the device."""
+    import torch
+    from . import restart
+    dm, ctx, lib, s = eng.dm, eng.ctx, eng.lib, eng.s
+    ops = restart.DeviceOps(dm, backend=eng.backend, A_host=A_host)
+    if norm_A is None:
+        norm_A = restart.normest(ops)
+    eng.nbreaks, eng.breaks, eng.norm_A = 0, [], norm_A
+    omega = None
+    tmp = torch.zeros((s + 1, eng.ld), dtype=torch.float64, device=eng.Q.device)
+    QR, nritz = None, 0
+    torch.cuda.synchronize(eng.Q.device)
+    for k in range(1, t + 1):
+        if k > 1:
+            extra = [(QR.data_ptr(), eng.ld, nritz)] if (orth == "selective" and nritz > 0) else []
+            eng.next_block(extra_blocks=extra)
+        T = eng.T                                                            # (s*k+1) x (s*k)
+        if orth == "periodic":
+            omega = update_omega(omega, np.diag(T, 0), np.diag(T, -1), norm_A, s)          # :433-436
+            err = 0.0
+            for i in range(1, s + 1):
+                row = omega[(k - 1) * s + i, : (k - 1) * s + i]
+                err = max(err, float(np.max(np.abs(row))) if row.size else 0.0)
+            if err >= np.sqrt(_EPS):                                         # :447-451
+                eng.nbreaks += 1
+                eng.breaks.append(k)
+                mold = (k - 1) * s
+                qb = (C.c_void_p * 1)(eng._qcol(0) if mold > 0 else None)
+                lds = (C.c_int64 * 1)(eng.ld)
+                mc = (C.c_int * 1)(mold)
+                s2, r2 = C.c_int(), C.c_int()
+                check(lib.calz_project_and_normalize(ctx.h, eng.n, 1, qb, lds, mc, s + 1, C.c_void_p(eng._qcol(mold)), eng.ld, 1,
+                                                     _lib.QR[eng.backend], C.c_void_p(tmp.data_ptr()), eng.ld, None, None,
+                                                     C.byref(s2), C.byref(r2)), ctx.h)
+                ctx.sync()
+                eng.Q[mold:mold + s + 1] = tmp                               # torch's stream; libcalz' stream is idle (synchronised)
+                torch.cuda.synchronize(eng.Q.device)
+                omega = reset_omega(omega, norm_A, s)
+        else:
+            m = s * k
+            Dp, Vp = np.linalg.eig(T[:m, :m])                                # :322
+            Vp = np.real(Vp)
+            conv = eng.b[k - 1] * np.abs(Vp[m - 1, :]) < norm_A * np.sqrt(_EPS)
+            if int(conv.sum()) > nritz:                                      # :330-341
+                eng.nbreaks += 1
+                eng.breaks.append(k)
+                nritz = int(conv.sum())
+                QRn = torch.zeros((nritz, eng.ld), dtype=torch.float64, device=eng.Q.device)
+                QRo = torch.zeros((nritz, eng.ld), dtype=torch.float64, device=eng.Q.device)
+                torch.cuda.synchronize(eng.Q.device)
+                cols = np.flatnonzero(conv)
+                for c0 in range(0, nritz, 16):                               # y = Q(:,1:k*s)*Vp(:,i): tall-skinny GEMM, 16 columns a call
+                    cc = min(16, nritz - c0)
+                    cf = np.asfortranarray(-Vp[:, cols[c0:c0 + cc]])
+                    check(lib.calz_block_axpy(ctx.h, eng.n, m, C.c_void_p(eng._qcol(0)), eng.ld, cc, cf.ctypes.data_as(_lib.c_dp), None,
+                                              eng.ld, C.c_void_p(QRn.data_ptr() + 8 * eng.ld * c0), eng.ld), ctx.h)
+                # QR(:,1:nritz) = normalize(QR(:,1:nritz))  (:340), 32 columns at most per QR call: wider sets are orthonormalised
+                # block by block (project against the finished ones, then normalize)
+                done = 0
+                while done < nritz:
+                    cc = min(32, nritz - done)
+                    src = QRn.data_ptr() + 8 * eng.ld * done
+                    dst = QRo.data_ptr() + 8 * eng.ld * done
+                    Rr = np.zeros((cc, cc), order="F")
+                    rk = C.c_int()
+                    if done == 0:
+                        check(lib.calz_normalize(ctx.h, eng.n, cc, C.c_void_p(src), eng.ld, _lib.QR[eng.backend], 1e-8, C.c_void_p(dst),
+                                                 eng.ld, Rr.ctypes.data_as(_lib.c_dp), C.byref(rk)), ctx.h)
+                    else:
+                        qb = (C.c_void_p * 1)(QRo.data_ptr()); lds = (C.c_int64 * 1)(eng.ld); mc = (C.c_int * 1)(done)
+                        s2 = C.c_int()
+                        check(lib.calz_project_and_normalize(ctx.h, eng.n, 1, qb, lds, mc, cc, C.c_void_p(src), eng.ld, 1,
+                                                             _lib.QR[eng.backend], C.c_void_p(dst), eng.ld, None, None, C.byref(s2),
+                                                             C.byref(rk)), ctx.h)
+                    done += cc
+                ctx.sync()
+                QR = QRo
+    eng.nritz = nritz
 
 
 # ----------------------------------------------------------------------------------------------- orthogonality (N2)

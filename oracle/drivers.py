@@ -102,12 +102,69 @@ def _extend_T(T, b, k, s, Bk, Rkk_s, Rk_s):
     return Tn
 
 
+# ----------------------------------------------------------------------------- ca_lanczos.m:469-551 (periodic orthogonalisation)
+EPS = np.finfo(np.float64).eps
+
+
+def update_omega(omega_in, alpha, beta, anorm, s):
+    """ca_lanczos.m:469-539 -- the omega recurrence (estimated loss of orthogonality) extended by s rows.  ``alpha``/``beta``:
+    diag(T,0) / diag(T,-1).  Written with 1-based index arrays (index 0 unused) so that every line reads like the reference."""
+    n = len(alpha)
+    al = np.concatenate([[0.0], np.asarray(alpha, dtype=np.float64)])
+    be = np.concatenate([[0.0], np.asarray(beta, dtype=np.float64)])
+    Tr = EPS * anorm                                                         # :476 "T = eps*anorm"
+    if omega_in is None or np.size(omega_in) == 0:
+        om = np.zeros((s + 2, s + 2))                                        # 1-based (s+1) x (s+1)
+        om[1, 1] = 1.0; om[1, 2] = 0.0
+        om[2, 1] = Tr / be[1]; om[2, 2] = 1.0
+        rng = range(2, s + 1)
+    else:
+        m = omega_in.shape[0] - 1
+        om = np.zeros((n + 2, n + 2))
+        om[1:m + 2, 1:m + 2] = omega_in
+        rng = range(m + 1, m + s + 1)
+    for j in rng:
+        binv = 1.0 / be[j]
+        om[j + 1, 1] = be[2] * om[j, 2] + (al[1] - al[j]) * om[j, 1] - be[j] * om[j - 1, 1]
+        om[j + 1, 1] = binv * (om[j + 1, 1] + Tr) if om[j + 1, 1] > 0 else binv * (om[j + 1, 1] - Tr)
+        for k in range(2, j):
+            om[j + 1, k] = be[k + 1] * om[j, k + 1] + (al[k] - al[j]) * om[j, k] + be[k] * om[j, k - 1] - be[j] * om[j - 1, k]
+            om[j + 1, k] = binv * (om[j + 1, k] + Tr) if om[j + 1, k] > 0 else binv * (om[j + 1, k] - Tr)
+        om[j + 1, j] = binv * Tr
+        om[j + 1, j + 1] = 1.0
+    return om[1:, 1:].copy()
+
+
+def reset_omega(omega_in, anorm, s):
+    """ca_lanczos.m:541-551."""
+    Tr = EPS * anorm
+    m = omega_in.shape[0] - s - 1
+    om = np.zeros((omega_in.shape[0] + 1, omega_in.shape[1] + 1))
+    om[1:, 1:] = omega_in
+    for j in range(m + 1, m + s + 1):
+        om[j + 1, 1:j + 1] = Tr
+        om[j + 1, j + 1] = 1.0
+    return om[1:, 1:].copy()
+
+
+def periodic_reorth_needed(omega, k, s):
+    """ca_lanczos.m:437-446: the largest estimated inner product of the s new vectors with everything before them."""
+    err = 0.0
+    for i in range(1, s + 1):
+        row = omega[(k - 1) * s + i, : (k - 1) * s + i]                      # omega((k-1)*s+i+1, 1:(k-1)*s+i), 0-based
+        err = max(err, float(np.max(np.abs(row))) if row.size else 0.0)
+    return err >= np.sqrt(EPS), err
+
+
 # ----------------------------------------------------------------------------- ca_lanczos.m
 def ca_lanczos(A, r, s, iter, basis, orth="local", K=_oracle_kernels, backend="tsqr", Bk=None, info=None):
-    """ca_lanczos.m:24-86 + ca_lanczos_basic :150-245 ('local' and 'full').  Returns (T, Q)."""
+    """ca_lanczos.m:24-86 + ca_lanczos_basic :150-245 ('local' and 'full'), ca_lanczos_selective :248-359,
+    ca_lanczos_periodic :362-467.  Returns (T, Q)."""
     orth = str(orth).lower()
+    if orth in ("periodic", "selective"):
+        return _ca_lanczos_periodic_selective(A, r, s, iter, basis, orth, K, backend, Bk, info)
     if orth not in ("local", "full"):
-        raise NotImplementedError("ca_lanczos orth=%s is out of scope" % orth)
+        raise ValueError("ERROR: Unknown orth type: " + orth)
     t = int(np.ceil(iter / s))
     q = r / np.sqrt(r @ r)
     if Bk is None:
@@ -140,6 +197,71 @@ def ca_lanczos(A, r, s, iter, basis, orth="local", K=_oracle_kernels, backend="t
     if info is not None:
         info["pan"] = log
         info["Bk"] = Bk
+    return np.asfortranarray(T[: s * t, : s * t]), Q[:, : s * t]
+
+
+def _ca_lanczos_periodic_selective(A, r, s, iter, basis, orth, K, backend, Bk, info):
+    """ca_lanczos_periodic (ca_lanczos.m:362-467) and ca_lanczos_selective (:248-359).  Note ``iter`` here is what the
+    dispatcher passes: t = ceil(iter/s) outer steps (:52,:80,:82)."""
+    t = int(np.ceil(iter / s))
+    q = r / np.sqrt(r @ r)
+    if Bk is None:
+        Bk = basis_matrix(A, q, s, basis, "full", K=K)
+    n = q.shape[0]
+    Q = np.zeros((n, t * s + 1), order="F")
+    Q[:, 0] = q
+    b = np.zeros(t + 1)
+    T = None
+    norm_A = normest(A)
+    omega = None
+    nbreaks, breaks, log = 0, [], []
+    QR = np.zeros((n, 0), order="F")                                         # selective: converged Ritz vectors
+    nritz = 0
+    for k in range(1, t + 1):
+        if k > 1:
+            q = Q[:, (k - 1) * s]
+        V = _matrix_powers(A, q, s, Bk, basis, K)
+        if k == 1:
+            Q[:, : s + 1], Rk, _ = K.normalize(V[:, : s + 1], backend=backend)
+            T = _mrdivide_upper(Rk @ Bk, Rk[:s, :s])
+            b[0] = T[s, s - 1]
+        else:
+            inf = {}
+            blocks = [Q[:, (k - 2) * s : (k - 1) * s + 1]]
+            if orth == "selective":
+                blocks.append(QR[:, :nritz] if nritz > 0 else None)          # :286  (an n x 0 block is an empty cell, project.m:33-38)
+            Q_, Rk_ = K.projectAndNormalize(blocks, V[:, 1 : s + 1], True, backend=backend, info=inf)
+            log.append(inf)
+            Rkk_s, Rk_s = Rk_[0], Rk_[-1]                                    # Rk_{1}, Rk_{2} (periodic) / Rk_{3} (selective)
+            Q[:, (k - 1) * s + 1 : k * s + 1] = Q_
+            T = _extend_T(T, b, k, s, Bk, Rkk_s, Rk_s)
+        if orth == "periodic":
+            alpha = np.diag(T, 0).copy()
+            beta = np.diag(T, -1).copy()
+            omega = update_omega(omega, alpha, beta, norm_A, s)              # :433-436
+            need, err = periodic_reorth_needed(omega, k, s)
+            if need:                                                         # :447-451
+                nbreaks += 1
+                breaks.append(k)
+                old = Q[:, : (k - 1) * s] if (k - 1) * s > 0 else None
+                Q[:, (k - 1) * s : k * s + 1], _ = K.projectAndNormalize([old], Q[:, (k - 1) * s : k * s + 1], True, backend=backend)
+                omega = reset_omega(omega, norm_A, s)
+        else:
+            Dp, Vp = np.linalg.eig(T[: s * k, : s * k])                      # :322
+            Dp, Vp = np.real(Dp), np.real(Vp)
+            conv = b[k - 1] * np.abs(Vp[s * k - 1, :]) < norm_A * np.sqrt(EPS)
+            if int(conv.sum()) > nritz:                                      # :330-341
+                nbreaks += 1
+                breaks.append(k)
+                nritz = int(conv.sum())
+                QR = np.asfortranarray(Q[:, : k * s] @ Vp[:, conv])
+                QR, _, _ = K.normalize(QR, backend=backend)
+    if info is not None:
+        info["pan"] = log
+        info["Bk"] = Bk
+        info["nbreaks"] = nbreaks
+        info["breaks"] = breaks
+        info["nritz"] = nritz
     return np.asfortranarray(T[: s * t, : s * t]), Q[:, : s * t]
 
 
