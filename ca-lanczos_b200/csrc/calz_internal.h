@@ -87,6 +87,7 @@ struct calz_ctx {
     int64_t opt_pan_fused_solve = 1; // tile pipeline, Cholesky back ends: downdated Gram + fused (update, triangular solve) last pass
     int64_t opt_mpk_dict_mode = -1;  // dictionary SELL: where the dictionary lives (0 shared memory, 2 constant bank, -1 by code uniformity)
     int64_t opt_mpk_halo_level = 0;  // depth of the ghost closure = MPK steps per halo exchange (0: automatic, see matrix.cu)
+    int64_t opt_mpk_fused_steps = 1; // dictionary SELL: all steps of an exchange group in one cooperative launch (grid barriers)
     int64_t opt_mpk_persist = 1;     // dictionary SELL: persistent, software-pipelined kernel (0 = one CTA per 16 slices)
     int64_t opt_sell_dict = 1;       // layout=auto may pick the dictionary-coded SELL variant
     int64_t opt_p2p = 1;             // peer-memory all-reduce / halo push instead of NCCL (when IPC works)

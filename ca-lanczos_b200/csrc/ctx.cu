@@ -240,6 +240,7 @@ int calz_set_option(calz_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "pan_fused_solve")) ctx->opt_pan_fused_solve = value;
     else if (!strcmp(key, "mpk_persist")) ctx->opt_mpk_persist = value;
     else if (!strcmp(key, "mpk_halo_level")) ctx->opt_mpk_halo_level = value;
+    else if (!strcmp(key, "mpk_fused_steps")) ctx->opt_mpk_fused_steps = value;
     else if (!strcmp(key, "mpk_dict_mode")) ctx->opt_mpk_dict_mode = value;
     else if (!strcmp(key, "mpk_xs_rows")) ctx->opt_mpk_xs_rows = value;
     else if (!strcmp(key, "tile_pipeline")) ctx->opt_tile_pipeline = value;

@@ -104,7 +104,7 @@ int calz_mat_destroy(calz_mat* m) {
     if (!m) return CALZ_OK;
     if (m->ctx) cudaStreamSynchronize(m->ctx->stream);
     p2p_halo_teardown(m);
-    void* ptrs[] = {m->d_long_row, m->d_long_seg0, m->d_long_segptr, m->d_long_segrow, m->d_long_col, m->d_long_val, m->d_long_part,
+    void* ptrs[] = {m->d_gridbar, m->d_long_row, m->d_long_seg0, m->d_long_segptr, m->d_long_segrow, m->d_long_col, m->d_long_val, m->d_long_part,
                     m->d_xs_off, m->d_codes, m->d_dict, m->d_send_idx, m->d_send_buf, m->d_rowptr, m->d_colind, m->d_val, m->d_slice_ptr,
                     m->d_sell_col, m->d_sell_val, m->d_perm, m->d_W_alloc};
     for (void* p : ptrs)

@@ -71,6 +71,9 @@ struct calz_mat {
     int xs_total = 0;                                 // doubles of shared memory for the segments
     int* d_xs_off = nullptr;                          // per code: position of x[row+offset] relative to (row - r0)
 
+    unsigned long long* d_gridbar = nullptr;           // grid-barrier counter of the fused MPK launch (monotonic)
+    unsigned long long gridbar_base = 0;
+
     // basis workspace n_loc x (s_max+1), ghosts included
     double* d_W = nullptr;                            // d_W_alloc + W_pad: (d_W + own_off) is 16-byte aligned
     double* d_W_alloc = nullptr;

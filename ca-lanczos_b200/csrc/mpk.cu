@@ -125,14 +125,13 @@ __device__ __forceinline__ void dict_fma8(const DictParam& P, uint32_t sbase, co
 // slice_ptr -> codes -> x is software pipelined (the slice pointers of item i+2 and the code words of item i+1 are in flight
 // while the x gathers of item i are issued).  !PERSIST: one work item per warp.  All indices are 32-bit (n_loc < 2^31 - 64;
 // slice_ptr carries one padding entry so that slice_ptr[s+2] is always readable).
+// one sweep y = A*x (+ Newton epilogue) over slices [slice_lo, slice_hi) by the whole grid; `sbase` from dict_stage
 template <bool NEWTON, bool PERSIST, int DM>
-__global__ void __launch_bounds__(kSpmvThreads, 5)
-k_spmv_selld(const int32_t* __restrict__ slice_ptr, const uint2* __restrict__ codes, const __grid_constant__ DictParam P,
-             const double* __restrict__ x, const double* __restrict__ xprev, double* __restrict__ y, int slice_lo,
-             int slice_hi, int n_loc, double shift, double pair) {
+__device__ __forceinline__ void selld_sweep(const int32_t* __restrict__ slice_ptr, const uint2* __restrict__ codes, const DictParam& P,
+                                            uint32_t sbase, const double* x, const double* xprev, double* y, int slice_lo, int slice_hi,
+                                            int n_loc, double shift, double pair) {
     constexpr int NS = kDictSlicesPerWarp;
     static_assert(NS == 2, "the pointer loads below fetch slice_ptr[s .. s+2]");
-    __shared__ __align__(4096) unsigned char sraw[DM == DM_CONST ? 16 : 4096];
     const int lane = threadIdx.x & 31;
     const int items = (slice_hi - slice_lo + NS - 1) / NS;
     const int stride = PERSIST ? (int)gridDim.x * (kSpmvThreads / 32) : items;
@@ -162,7 +161,6 @@ k_spmv_selld(const int32_t* __restrict__ slice_ptr, const uint2* __restrict__ co
     load_ptrs(it, p0, nb);
     if (PERSIST) load_ptrs(it + stride, p0n, nbn);
     load_codes(p0, nb, 0, w);
-    const uint32_t sbase = dict_stage<DM>(sraw, P);
     for (; it < items; it += stride) {
         uint2 wn[NS];
         int32_t p0nn[NS], nbnn[NS];
@@ -201,6 +199,55 @@ k_spmv_selld(const int32_t* __restrict__ slice_ptr, const uint2* __restrict__ co
                 p0n[i] = p0nn[i]; nbn[i] = nbnn[i];
             }
         }
+    }
+}
+
+template <bool NEWTON, bool PERSIST, int DM>
+__global__ void __launch_bounds__(kSpmvThreads, 5)
+k_spmv_selld(const int32_t* __restrict__ slice_ptr, const uint2* __restrict__ codes, const __grid_constant__ DictParam P,
+             const double* __restrict__ x, const double* __restrict__ xprev, double* __restrict__ y, int slice_lo,
+             int slice_hi, int n_loc, double shift, double pair) {
+    __shared__ __align__(4096) unsigned char sraw[DM == DM_CONST ? 16 : 4096];
+    const uint32_t sbase = dict_stage<DM>(sraw, P);
+    selld_sweep<NEWTON, PERSIST, DM>(slice_ptr, codes, P, sbase, x, xprev, y, slice_lo, slice_hi, n_loc, shift, pair);
+}
+
+// ---- the matrix powers kernel proper: ALL steps of one exchange group in ONE cooperative launch.  Step k sweeps the slices
+//      [lo_k, hi_k) of column k-1 -> column k of the basis workspace; a grid-wide barrier (one atomic per CTA on a monotonically
+//      increasing 64-bit counter, release/acquire fences) separates the steps.  No column is read before it is written inside the
+//      launch, so the L1-cached x gathers of the single-step kernel stay valid.  Same arithmetic, same order: bit-identical.
+constexpr int kMpkMaxSteps = 32;
+struct MpkSteps {
+    int nsteps, col0;                     // step i reads column col0 + i, writes column col0 + i + 1
+    int lo[kMpkMaxSteps], hi[kMpkMaxSteps];
+    double shift[kMpkMaxSteps], pair[kMpkMaxSteps];
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned long long* counter, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1ull);
+        while (*(volatile unsigned long long*)counter < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <bool NEWTON, int DM>
+__global__ void __launch_bounds__(kSpmvThreads, 5)
+k_mpk_selld(const int32_t* __restrict__ slice_ptr, const uint2* __restrict__ codes, const __grid_constant__ DictParam P,
+            double* W, long long ldW, const __grid_constant__ MpkSteps st, int n_loc, unsigned long long* counter,
+            unsigned long long base) {
+    __shared__ __align__(4096) unsigned char sraw[DM == DM_CONST ? 16 : 4096];
+    const uint32_t sbase = dict_stage<DM>(sraw, P);
+    for (int i = 0; i < st.nsteps; ++i) {
+        const int col = st.col0 + i;
+        const double* x = W + (long long)col * ldW;
+        const double* xp = col >= 1 ? W + (long long)(col - 1) * ldW : x;
+        selld_sweep<NEWTON, true, DM>(slice_ptr, codes, P, sbase, x, xp, W + (long long)(col + 1) * ldW, st.lo[i], st.hi[i], n_loc,
+                                      st.shift[i], st.pair[i]);
+        if (i + 1 < st.nsteps) grid_barrier(counter, base + (unsigned long long)gridDim.x * (i + 1));
     }
 }
 
@@ -433,6 +480,48 @@ int launch_selld(calz_mat* m, const double* x, const double* xp, double* y, int6
 
 int spmv_main(calz_mat* m, const double* x, const double* xp, double* y, int64_t lo, int64_t hi, bool newton, double shift, double pair);
 
+// steps k0 .. k0+ns-1 (1-based) of the MPK in one cooperative launch (dictionary layout, persistent grid)
+template <bool NEWTON, int DM>
+int launch_mpk_selld_t(calz_mat* m, const MpkSteps& st) {
+    calz_ctx* ctx = m->ctx;
+    static int occ = 0;
+    if (!occ) {
+        CALZ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mpk_selld<NEWTON, DM>, kSpmvThreads, 0));
+        if (occ < 1) occ = 1;
+    }
+    int maxs = 0;
+    for (int i = 0; i < st.nsteps; ++i) maxs = std::max(maxs, st.hi[i] - st.lo[i]);
+    const int64_t per_cta = (int64_t)(kSpmvThreads / 32) * kDictSlicesPerWarp;
+    unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((maxs + per_cta - 1) / per_cta, (int64_t)ctx->num_sms * occ));
+    if (!m->d_gridbar) {
+        CALZ_CUDA(ctx, cudaMalloc(&m->d_gridbar, 64));
+        CALZ_CUDA(ctx, cudaMemsetAsync(m->d_gridbar, 0, 64, ctx->stream));
+        m->gridbar_base = 0;
+    }
+    const int32_t* sp = m->d_slice_ptr;
+    const uint2* codes = (const uint2*)m->d_codes;
+    DictParam* P = (DictParam*)m->h_dict;
+    double* W = m->d_W;
+    long long ld = m->ldW;
+    int n_loc = (int)m->n_loc;
+    unsigned long long* ctr = m->d_gridbar;
+    unsigned long long base = m->gridbar_base;
+    MpkSteps stc = st;
+    void* args[] = {(void*)&sp, (void*)&codes, (void*)P, (void*)&W, (void*)&ld, (void*)&stc, (void*)&n_loc, (void*)&ctr, (void*)&base};
+    CALZ_CUDA(ctx, cudaLaunchCooperativeKernel((const void*)k_mpk_selld<NEWTON, DM>, dim3(grid), dim3(kSpmvThreads), args, 0, ctx->stream));
+    ctx->launches++;
+    m->gridbar_base += (unsigned long long)grid * (unsigned long long)(st.nsteps - 1);
+    return CALZ_OK;
+}
+
+int launch_mpk_selld(calz_mat* m, const MpkSteps& st, bool newton) {
+    calz_ctx* ctx = m->ctx;
+    int dm = (int)ctx->opt_mpk_dict_mode;
+    if (dm < 0) dm = m->dict_uniform >= 0.75 ? DM_CONST : DM_SHARED;
+    if (dm == DM_CONST) return newton ? launch_mpk_selld_t<true, DM_CONST>(m, st) : launch_mpk_selld_t<false, DM_CONST>(m, st);
+    return newton ? launch_mpk_selld_t<true, DM_SHARED>(m, st) : launch_mpk_selld_t<false, DM_SHARED>(m, st);
+}
+
 // one SpMV step on local rows [lo,hi) (already aligned to the layout granule)
 int spmv_step(calz_mat* m, const double* x, const double* xp, double* y, int64_t lo, int64_t hi, bool newton,
               double shift, double pair) {
@@ -595,7 +684,27 @@ int mpk_run(calz_mat* m, const double* v, int s, const Shifts& sh) {
         chunk_rows = round_up(std::max<int64_t>(ctx->opt_l2_chunk_bytes / bytes_per_row, gran), gran);
         if (chunk_rows < 2 * bwid || chunk_rows >= m->n_loc) chunk_rows = 0;   // band too wide / matrix fits: plain sweeps
     }
-    if (chunk_rows == 0) {
+    const bool fused = chunk_rows == 0 && m->layout == CALZ_LAYOUT_SELL_DICT && ctx->opt_mpk_fused_steps && ctx->opt_mpk_persist &&
+                       !(m->xs_rows > 0 && ctx->opt_mpk_tma_x && m->W_pad == 0) && m->n_long == 0 && s <= kMpkMaxSteps;
+    if (fused) {
+        // all steps of an exchange group in ONE cooperative launch (grid barrier between steps)
+        for (int k0 = 1; k0 <= s; k0 += L) {
+            const int ns = std::min(L, s - k0 + 1);
+            CALZ_TRY(exchange_before(k0));
+            MpkSteps st{};
+            st.nsteps = ns;
+            st.col0 = k0 - 1;
+            for (int i = 0; i < ns; ++i) {
+                const int k = k0 + i;
+                st.lo[i] = (int)(lo_of(k) / 32);
+                st.hi[i] = (int)((hi_of(k) + 31) / 32);
+                st.shift[i] = sh.newton ? sh.re[k - 1] : 0.0;
+                st.pair[i] = sh.newton ? sh.pair[k - 1] : 0.0;
+            }
+            CALZ_TRY(launch_mpk_selld(m, st, sh.newton));
+            CALZ_TRY(ack_after(k0));
+        }
+    } else if (chunk_rows == 0) {
         for (int k = 1; k <= s; ++k) {
             CALZ_TRY(exchange_before(k));
             CALZ_TRY(step(k, 0, m->n_loc));

@@ -107,7 +107,7 @@ def powerlaw_spd(n: int, avg_deg: float = 20.0, seed: int = 0, alpha: float = 0.
 
 
 def powerlaw_spd_rows(n: int, avg_deg: float = 20.0, seed: int = 0, alpha: float = 0.8, row_lo: int = 0, row_hi: int | None = None,
-                      shuffle: bool = True, chunk: int = 1 << 23) -> sp.csr_matrix:
+                      shuffle: bool = True, chunk: int = 1 << 23, jacobi: bool = False) -> sp.csr_matrix:
     """Rows [row_lo,row_hi) of the C4 matrix at scale (n = 2e7, nnz ~ 4e8), generated WITHOUT the other rows: the edge
     list is produced chunk by chunk from a counter-seeded generator (every rank generates the same chunks and keeps the
     edges that touch its rows), so host memory stays bounded by the rank's own share.
@@ -117,7 +117,12 @@ def powerlaw_spd_rows(n: int, avg_deg: float = 20.0, seed: int = 0, alpha: float
     rank meets the edges: the matrix is exactly symmetric and exactly the same for every partition), symmetrised, duplicates summed, diagonal = sum|row| + 1 (strictly diagonally dominant => SPD).  ``shuffle``
     relabels the vertices by the affine permutation pi(r) = (a*r + b) mod n (a coprime to n): the spectrum is unchanged, but
     the hubs are spread over the row partition instead of all landing on rank 0 (the contiguous-block partition of the north
-    star is fixed; a power-law graph in degree order would put ~40 % of the non-zeros on the first of 8 ranks)."""
+    star is fixed; a power-law graph in degree order would put ~40 % of the non-zeros on the first of 8 ranks).
+
+    ``jacobi``: return D^-1/2 A D^-1/2 (D = diag A; unit diagonal, spectrum in (0,2), still SPD, same pattern).  The unscaled
+    matrix is L + I with L a weighted graph Laplacian: ones(n,1) is an exact eigenvector and one eigenvalue per hub dwarfs the
+    rest of the spectrum, on which the s = 6 basis blocks of the reference are numerically rank deficient (oracle: rank 3 of 6
+    in the second block) -- the scaled matrix is the one bench.py --config c4 solves."""
     n = int(n)
     row_hi = n if row_hi is None else int(row_hi)
     m = int(n * avg_deg / 2)
@@ -129,6 +134,7 @@ def powerlaw_spd_rows(n: int, avg_deg: float = 20.0, seed: int = 0, alpha: float
     b_add = n // 3
     rows, cols, vals = [], [], []
     expo = 1.0 / (1.0 - alpha)
+    dsum = np.zeros(n) if jacobi else None          # sum |row| of EVERY row (the scaling needs the diagonal of every column)
     for c0 in range(0, m, chunk):
         cnt = min(chunk, m - c0)
         rng = np.random.default_rng([int(seed), c0 // chunk])
@@ -138,6 +144,8 @@ def powerlaw_spd_rows(n: int, avg_deg: float = 20.0, seed: int = 0, alpha: float
         if shuffle:
             i = (i * a_mul + b_add) % n
         keep = i != j
+        if jacobi:
+            dsum += np.bincount(i[keep], weights=-v[keep], minlength=n) + np.bincount(j[keep], weights=-v[keep], minlength=n)
         mi = keep & (i >= row_lo) & (i < row_hi)
         mj = keep & (j >= row_lo) & (j < row_hi)
         rows += [i[mi], j[mj]]; cols += [j[mi], i[mj]]; vals += [v[mi], v[mj]]
@@ -146,6 +154,12 @@ def powerlaw_spd_rows(n: int, avg_deg: float = 20.0, seed: int = 0, alpha: float
     del rows, cols, vals
     d = -np.asarray(B.sum(axis=1)).ravel() + 1.0                                     # all off-diagonal values are negative
     nloc = row_hi - row_lo
+    if jacobi:
+        di = 1.0 / np.sqrt(dsum + 1.0)
+        B.sort_indices()
+        rr = np.repeat(np.arange(row_lo, row_hi, dtype=np.int64), np.diff(B.indptr))
+        B.data = B.data * (di[rr] * di[B.indices])                                   # symmetric: the two factors commute
+        d = np.ones(nloc)
     D = sp.csr_matrix((d, np.arange(row_lo, row_hi, dtype=np.int64), np.arange(nloc + 1, dtype=np.int64)), shape=(nloc, n))
     A = (B + D).tocsr()
     A.sort_indices()
