@@ -90,6 +90,7 @@ struct calz_ctx {
     int64_t opt_mpk_fused_steps = 1; // dictionary SELL: all steps of an exchange group in one cooperative launch (grid barriers)
     int64_t opt_mpk_persist = 1;     // dictionary SELL: persistent, software-pipelined kernel (0 = one CTA per 16 slices)
     int64_t opt_sell_dict = 1;       // layout=auto may pick the dictionary-coded SELL variant
+    int64_t opt_fused_allreduce = 1; // tile passes: the finalize launch is the peer-memory all-reduce as well
     int64_t opt_p2p = 1;             // peer-memory all-reduce / halo push instead of NCCL (when IPC works)
     calz::P2P p2p;
     int64_t opt_tile_pipeline = 1;   // fused TMA-tile passes in projectAndNormalize (0: legacy kernels)

@@ -235,6 +235,7 @@ int calz_set_option(calz_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "csr_lanes")) ctx->opt_csr_lanes = value;
     else if (!strcmp(key, "cholqr2_inv_thresh")) ctx->opt_cholqr2_inv_thresh = value > 0 ? value : 32;
     else if (!strcmp(key, "p2p")) ctx->opt_p2p = value;
+    else if (!strcmp(key, "fused_allreduce")) ctx->opt_fused_allreduce = value;
     else if (!strcmp(key, "sell_dict")) ctx->opt_sell_dict = value;
     else if (!strcmp(key, "mpk_tma_x")) ctx->opt_mpk_tma_x = value;
     else if (!strcmp(key, "pan_fused_solve")) ctx->opt_pan_fused_solve = value;

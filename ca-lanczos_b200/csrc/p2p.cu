@@ -14,36 +14,11 @@
 #include <string.h>
 
 #include "matrix.h"
+#include "p2p_dev.cuh"
 
 namespace calz {
 
 namespace {
-
-constexpr unsigned long long kSpinLimit = 20ull * 1000ull * 1000ull;      // ~10-20 s; a healthy wait is microseconds
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ bool spin_until(const unsigned long long* flag, unsigned long long seq, int* err) {
-    unsigned long long it = 0;
-    while (ld_acquire_sys(flag) < seq) {
-        if (++it > kSpinLimit || (it % 4096 == 0 && *(volatile int*)err)) {
-            *(volatile int*)err = 1;
-            return false;
-        }
-    }
-    return true;
-}
-
-struct PeerPtrs {
-    double* mbox[kMaxPeers];
-    unsigned long long* flags[kMaxPeers];
-};
 
 // in place: data[i] = sum_r contribution_r[i], r in rank order
 __global__ void __launch_bounds__(256)
@@ -166,8 +141,8 @@ int p2p_setup(calz_ctx* ctx) {
     p.flags = (unsigned long long*)((char*)p.base + mbox_bytes);
     CALZ_CUDA(ctx, cudaMalloc(&p.err, 64));
     CALZ_CUDA(ctx, cudaMemset(p.err, 0, 64));
-    CALZ_CUDA(ctx, cudaMalloc(&p.tickets, kMaxPeers * sizeof(unsigned int)));
-    CALZ_CUDA(ctx, cudaMemset(p.tickets, 0, kMaxPeers * sizeof(unsigned int)));
+    CALZ_CUDA(ctx, cudaMalloc(&p.tickets, 2 * kMaxPeers * sizeof(unsigned int)));
+    CALZ_CUDA(ctx, cudaMemset(p.tickets, 0, 2 * kMaxPeers * sizeof(unsigned int)));
     cudaIpcMemHandle_t mine;
     cudaError_t e = cudaIpcGetMemHandle(&mine, p.base);
     int ok = (e == cudaSuccess) ? 1 : 0;
@@ -232,6 +207,21 @@ int p2p_allreduce(calz_ctx* ctx, double* dev, size_t count) {
     k_allreduce_p2p<<<1, 256, 0, ctx->stream>>>(dev, (int)count, ctx->nranks, ctx->rank, seq, pp, p.mbox, p.flags, p.err);
     CALZ_LAUNCH_CHECK(ctx);
     return CALZ_OK;
+}
+
+void p2p_next_allreduce(calz_ctx* ctx, ArArgs* a) {
+    P2P& p = ctx->p2p;
+    a->P = ctx->nranks;
+    a->me = ctx->rank;
+    for (int q = 0; q < ctx->nranks; ++q) {
+        a->peers.mbox[q] = (double*)p.peer_base[q];
+        a->peers.flags[q] = (unsigned long long*)((char*)p.peer_base[q] + mbox_bytes_total());
+    }
+    a->seq = ++p.seq_allreduce;
+    a->my_mbox = p.mbox;
+    a->my_flags = p.flags;
+    a->err = p.err;
+    a->ticket = p.tickets + kMaxPeers;          // its own ticket word (the halo push uses [0, kMaxPeers))
 }
 
 int p2p_check(calz_ctx* ctx) {      // after a synchronisation: did any bounded spin give up?

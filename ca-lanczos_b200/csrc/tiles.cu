@@ -16,6 +16,7 @@
 // Reductions are deterministic: fixed warp order inside the CTA, per-CTA partials, last CTA sums them in a fixed order.
 #include <algorithm>
 
+#include "p2p_dev.cuh"
 #include "tsops.cuh"
 
 namespace calz {
@@ -185,19 +186,24 @@ k_tile(TileArgs p, int stages) {
             if (MODE != MODE_COEFF) {
                 // ---- Y = X - Q*C on the tensor pipe, warp-local: the warp updates the SAME 16 rows it contracts below, so no
                 //      CTA-wide barrier is needed.  Per 8-row group: D(8 cols x 8 rows) = X' + (-C')(8 x K) * Q'(K x 8 rows);
-                //      thread (g, tq) holds D[col g][rows 2tq, 2tq+1], A[col g][k tq] = -C(k, col), B[k tq][row g] = Q(row, k).
+                //      thread (g, tq) holds D[col g][n = 2tq, 2tq+1], A[col g][k tq] = -C(k, col), B[k tq][n g] = Q(row, k).
+                //      The n index of the fragment is mapped to the tile row rho(n) = {0,1,2,3,5,4,7,6}[n]: with the 132-double
+                //      column pitch this makes the D-fragment accesses (two 8-byte words per thread, rows rho(2tq), rho(2tq+1))
+                //      AND the B-fragment accesses (row rho(g)) bank-conflict free (a double2 at rows 2tq, 2tq+1 collided 2-way).
+                const int rho_g = g ^ (g >> 2);                                  // rho(g):  0 1 2 3 5 4 7 6
+                const int rho0 = 2 * tq + (tq >> 1), rho1 = 2 * tq + 1 - (tq >> 1);   // rho(2tq) = 0 2 5 7, rho(2tq+1) = 1 3 4 6
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int rbase = 16 * warp + 8 * h;
                     double d[CT][2], bq[2 * MT];
 #pragma unroll
                     for (int b = 0; b < CT; ++b) {
-                        const double2 xv = *reinterpret_cast<const double2*>(&T[(size_t)(8 * MT + 8 * b + g) * kPitch + rbase + 2 * tq]);
-                        d[b][0] = xv.x;
-                        d[b][1] = xv.y;
+                        const double* xs = &T[(size_t)(8 * MT + 8 * b + g) * kPitch + rbase];
+                        d[b][0] = xs[rho0];
+                        d[b][1] = xs[rho1];
                     }
 #pragma unroll
-                    for (int ks = 0; ks < 2 * MT; ++ks) bq[ks] = T[(size_t)(4 * ks + tq) * kPitch + rbase + g];
+                    for (int ks = 0; ks < 2 * MT; ++ks) bq[ks] = T[(size_t)(4 * ks + tq) * kPitch + rbase + rho_g];
 #pragma unroll
                     for (int ks = 0; ks < 2 * MT; ++ks)
 #pragma unroll
@@ -210,12 +216,14 @@ k_tile(TileArgs p, int stages) {
                     }
 #pragma unroll
                     for (int b = 0; b < CT; ++b) {
-                        *reinterpret_cast<double2*>(&T[(size_t)(8 * MT + 8 * b + g) * kPitch + rbase + 2 * tq]) = make_double2(d[b][0], d[b][1]);
+                        double* xs = &T[(size_t)(8 * MT + 8 * b + g) * kPitch + rbase];
+                        xs[rho0] = d[b][0];
+                        xs[rho1] = d[b][1];
                         if (!SOLVE && p.Y && 8 * b + g < p.c) {
-                            const long long r = r0 + rbase + 2 * tq;
+                            const long long r = r0 + rbase;
                             double* dst = p.Y + (long long)(8 * b + g) * p.ldY + r;
-                            if (r + 1 < p.n) *reinterpret_cast<double2*>(dst) = make_double2(d[b][0], d[b][1]);
-                            else if (r < p.n) *dst = d[b][0];
+                            if (r + rho0 < p.n) dst[rho0] = d[b][0];
+                            if (r + rho1 < p.n) dst[rho1] = d[b][1];
                         }
                     }
                 }
@@ -308,14 +316,90 @@ k_tile(TileArgs p, int stages) {
     }
 }
 
+template <int MT, int CT, int MODE>
+__device__ __forceinline__ double tile_partial_sum(const double* __restrict__ partials, int nparts, int e, int lane) {
+    constexpr int RT0 = (MODE == MODE_UPDATE_GRAM) ? MT : 0;
+    constexpr int ELEMS = (MT + CT - RT0) * CT * 64;
+    double sum = 0.0;
+    for (int b0 = lane; b0 < nparts; b0 += 32 * 16) {
+        double v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int b = b0 + 32 * q;
+            v[q] = b < nparts ? partials[(size_t)b * ELEMS + e] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) sum += v[q];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    return sum;
+}
+
+template <int MT, int CT, int MODE>
+__device__ __forceinline__ void tile_finalize_ar(const double* __restrict__ partials, int nparts, double* __restrict__ S, int ldS, int M,
+                                                 int c, const ArArgs& ar) {
+    constexpr int RT0 = (MODE == MODE_UPDATE_GRAM) ? MT : 0;
+    constexpr int NRT = MT + CT - RT0;
+    constexpr int ELEMS = NRT * CT * 64;
+    const int lane = threadIdx.x & 31;
+    const int e = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int buf = (int)(ar.seq % kMboxBufs);
+    const size_t slot = ((size_t)buf * kMaxPeers + ar.me) * kMboxSlot;
+    if (e < ELEMS) {
+        const int tl = e >> 6, i = (e >> 3) & 7, j = e & 7;
+        const int rt = RT0 + tl / CT, ct = tl % CT;
+        const int col = 8 * ct + j;
+        int rowS;
+        bool valid;
+        if (rt < MT) { rowS = 8 * rt + i; valid = rowS < M; }
+        else { const int k = 8 * (rt - MT) + i; rowS = M + k; valid = k < c; }
+        if (valid && col < c) {
+            const double sum = tile_partial_sum<MT, CT, MODE>(partials, nparts, e, lane);
+            if (lane < ar.P) ar.peers.mbox[lane][slot + (size_t)col * ldS + rowS] = sum;       // one peer per lane
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ int s_last, s_ok;
+    if (threadIdx.x == 0) {
+        s_last = (atomicAdd(ar.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+        s_ok = 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) *ar.ticket = 0;
+    __threadfence_system();
+    if (threadIdx.x < ar.P) st_release_sys(ar.peers.flags[threadIdx.x] + kFlagAllreduce + buf * kMaxPeers + ar.me, ar.seq);
+    if (threadIdx.x < ar.P && !spin_until(ar.my_flags + kFlagAllreduce + buf * kMaxPeers + threadIdx.x, ar.seq, ar.err)) s_ok = 0;
+    __syncthreads();
+    if (!s_ok) return;
+    const int count = ldS * c;
+    for (int idx = threadIdx.x; idx < count; idx += blockDim.x) {
+        const int rowS = idx % ldS;
+        if (MODE == MODE_UPDATE_GRAM && rowS < M) continue;                                  // only the block part is produced
+        double s = 0.0;
+        for (int r = 0; r < ar.P; ++r) s += __ldcv(ar.my_mbox + ((size_t)buf * kMaxPeers + r) * kMboxSlot + idx);
+        S[idx] = s;
+    }
+}
+
 // Deterministic second stage of the reduction: one warp per element of S sums the per-CTA partials in a fixed order
 // (lanes stride over the CTAs with all loads in flight at once, fixed shuffle tree).  A separate small launch on purpose:
 // done by the last CTA of k_tile it cost ~30 us of serialised L2 latency per pass.
+// With a communicator (ar.P > 1) the same launch is the all-reduce as well (peer-memory mailbox, see p2p.cu): every element goes
+// straight into slot [seq % 4][me] of EVERY rank's mailbox instead of into S; the last CTA to finish raises this rank's flag at
+// all peers, waits for theirs and writes S = sum over ranks (rank order: identical bits everywhere).  One launch instead of
+// finalize + all-reduce, and the local sums never make the round trip through S.
 template <int MT, int CT, int MODE>
 __global__ void __launch_bounds__(256)
 k_tile_finalize(const double* __restrict__ partials, int nparts, double* __restrict__ S, int ldS, int M, int c,
-                const int* __restrict__ pred, int want) {
+                const int* __restrict__ pred, int want, const __grid_constant__ ArArgs ar) {
     if (pred && *pred != want) return;
+    if (ar.P > 1) {
+        tile_finalize_ar<MT, CT, MODE>(partials, nparts, S, ldS, M, c, ar);
+        return;
+    }
     constexpr int RT0 = (MODE == MODE_UPDATE_GRAM) ? MT : 0;
     constexpr int NRT = MT + CT - RT0;
     constexpr int ELEMS = NRT * CT * 64;
@@ -330,24 +414,12 @@ k_tile_finalize(const double* __restrict__ partials, int nparts, double* __restr
     if (rt < MT) { rowS = 8 * rt + i; valid = rowS < M; }
     else { const int k = 8 * (rt - MT) + i; rowS = M + k; valid = k < c; }
     if (!valid || col >= c) return;
-    double sum = 0.0;
-    for (int b0 = lane; b0 < nparts; b0 += 32 * 16) {
-        double v[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int b = b0 + 32 * q;
-            v[q] = b < nparts ? partials[(size_t)b * ELEMS + e] : 0.0;
-        }
-#pragma unroll
-        for (int q = 0; q < 16; ++q) sum += v[q];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const double sum = tile_partial_sum<MT, CT, MODE>(partials, nparts, e, lane);
     if (lane == 0) S[(size_t)col * ldS + rowS] = sum;
 }
 
 template <int MT, int CT, int MODE>
-int launch_tile(calz_ctx* ctx, const TileArgs& a0) {
+int launch_tile(calz_ctx* ctx, const TileArgs& a0, bool fuse_allreduce = false) {
     TileArgs a = a0;
     constexpr int SLOTS = 8 * (MT + CT);
     constexpr bool SOLVE = (MODE == MODE_UPDATE_SOLVE);
@@ -380,7 +452,10 @@ int launch_tile(calz_ctx* ctx, const TileArgs& a0) {
     kern<<<grid, kTileThreads, smem, ctx->stream>>>(a, stages);
     CALZ_LAUNCH_CHECK(ctx);
     if (SOLVE) return CALZ_OK;
-    k_tile_finalize<MT, CT, MODE><<<(NRT * CT * 64 + 7) / 8, 256, 0, ctx->stream>>>(a.partials, grid, a.S, a.ldS, a.M, a.c, a.pred, a.want);
+    ArArgs ar{};
+    ar.P = 1;
+    if (fuse_allreduce) p2p_next_allreduce(ctx, &ar);
+    k_tile_finalize<MT, CT, MODE><<<(NRT * CT * 64 + 7) / 8, 256, 0, ctx->stream>>>(a.partials, grid, a.S, a.ldS, a.M, a.c, a.pred, a.want, ar);
     CALZ_LAUNCH_CHECK(ctx);
     return CALZ_OK;
 }
@@ -401,17 +476,21 @@ int tile_pass(calz_ctx* ctx, int mode, int64_t n, const double* Q, int64_t ldQ, 
     a.S = S_dev; a.ldS = ldS; a.pred = pred; a.want = want;
     const int MT = (M + 7) / 8, CT = (c + 7) / 8;
     int st;
+    // with a communicator and the peer-memory mailbox available the finalize launch is the all-reduce too.  Not for a predicated
+    // pass: a skipped launch would leave the peers waiting (the generic all-reduce below always runs).
+    const bool fuse_ar = allreduce && ctx->nranks > 1 && !pred && ldS == M + c && p2p_allreduce_ok(ctx, (size_t)ldS * c) &&
+                         ctx->opt_fused_allreduce;
 #define CALZ_TILE(MTv, CTv)                                                         \
-    st = mode == 0 ? launch_tile<MTv, CTv, MODE_COEFF>(ctx, a)                      \
-       : mode == 1 ? launch_tile<MTv, CTv, MODE_UPDATE_FULL>(ctx, a)                \
-                   : launch_tile<MTv, CTv, MODE_UPDATE_GRAM>(ctx, a)
+    st = mode == 0 ? launch_tile<MTv, CTv, MODE_COEFF>(ctx, a, fuse_ar)             \
+       : mode == 1 ? launch_tile<MTv, CTv, MODE_UPDATE_FULL>(ctx, a, fuse_ar)       \
+                   : launch_tile<MTv, CTv, MODE_UPDATE_GRAM>(ctx, a, fuse_ar)
     if (MT == 1 && CT == 1) { CALZ_TILE(1, 1); }
     else if (MT == 2 && CT == 1) { CALZ_TILE(2, 1); }
     else if (MT == 1 && CT == 2) { CALZ_TILE(1, 2); }
     else { CALZ_TILE(2, 2); }
 #undef CALZ_TILE
     CALZ_TRY(st);
-    if (allreduce && ctx->nranks > 1) {
+    if (allreduce && ctx->nranks > 1 && !fuse_ar) {
         // a predicated-off pass leaves S untouched on every rank alike, so the collective stays consistent
         if (mode == 2) {
             if (ldS != M + c) return set_error(ctx, CALZ_ERR_BADARG, "tile_pass: dense S expected");
