@@ -35,6 +35,15 @@ SIGNATURES = {
     "calz_sync": (C.c_int, [c_vp]),
     "calz_launch_count": (c_i64, [c_vp, C.c_int]),
     "calz_set_option": (C.c_int, [c_vp, C.c_char_p, c_i64]),
+    "calz_shared_context": (C.c_int, [C.POINTER(c_vp)]),
+    "calz_shared_release": (C.c_int, []),
+    "calz_mat_cache_get_csc64": (C.c_int, [c_vp, c_i64, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), c_dp, C.c_int, C.c_int, C.POINTER(c_vp)]),
+    "calz_mat_cache_clear": (C.c_int, [c_vp]),
+    "calz_vec_create": (C.c_int, [c_vp, c_i64, C.c_int, C.POINTER(c_vp)]),
+    "calz_vec_destroy": (C.c_int, [c_vp]),
+    "calz_vec_info": (C.c_int, [c_vp, C.POINTER(c_vp), c_i64p, c_ip, c_i64p]),
+    "calz_vec_upload": (C.c_int, [c_vp, C.c_int, C.c_int, c_dp, c_i64]),
+    "calz_vec_download": (C.c_int, [c_vp, C.c_int, C.c_int, c_dp, c_i64]),
     "calz_comm_unique_id": (C.c_int, [C.c_char_p, C.c_char_p]),
     "calz_comm_init": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_char_p, C.c_char_p]),
     "calz_comm_rank": (C.c_int, [c_vp, c_ip, c_ip]),

@@ -4,9 +4,12 @@
 #include <stdarg.h>
 #include <string.h>
 
-#include <algorithm>
+#include <stdlib.h>
 
-#include "calz_internal.h"
+#include <algorithm>
+#include <vector>
+
+#include "matrix.h"
 
 namespace calz {
 
@@ -247,6 +250,148 @@ int calz_set_option(calz_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "tile_pipeline")) ctx->opt_tile_pipeline = value;
     else if (!strcmp(key, "grid_mult")) ctx->opt_grid_mult = value > 0 ? value : 1;
     else return set_error(ctx, CALZ_ERR_BADARG, "calz_set_option: unknown key '%s'", key);
+    return CALZ_OK;
+}
+
+// ---- process-wide context + device-matrix cache (the MEX gateways' shared state)
+namespace {
+struct CachedMat { const void* pr; int64_t n; uint64_t nnz, fp; int s_max, layout; calz_mat* m; };
+calz_ctx* g_shared_ctx = nullptr;
+std::vector<CachedMat> g_mat_cache;
+
+uint64_t fnv(uint64_t h, const void* p, size_t bytes) {
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < bytes; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
+// 4096 strided samples of each array plus 64 entries at both ends: O(1) per call, catches a rebuilt matrix at a reused address
+uint64_t csc_fingerprint(int64_t n, uint64_t nnz, const uint64_t* jc, const uint64_t* ir, const double* pr) {
+    uint64_t h = 1469598103934665603ull;
+    auto sample = [&](const void* base, size_t count, size_t elem) {
+        if (!count) return;
+        const size_t step = std::max<size_t>(1, count / 4096);
+        for (size_t i = 0; i < count; i += step) h = fnv(h, (const char*)base + i * elem, elem);
+        const size_t edge = std::min<size_t>(64, count);
+        h = fnv(h, base, edge * elem);
+        h = fnv(h, (const char*)base + (count - edge) * elem, edge * elem);
+    };
+    sample(jc, (size_t)n + 1, 8);
+    sample(ir, (size_t)nnz, 8);
+    sample(pr, (size_t)nnz, 8);
+    return h;
+}
+}  // namespace
+
+int calz_shared_context(calz_ctx** ctx) {
+    if (!ctx) return set_error(nullptr, CALZ_ERR_BADARG, "calz_shared_context: ctx is NULL");
+    if (!g_shared_ctx) {
+        const char* dev = getenv("CALZ_DEVICE");
+        CALZ_TRY(calz_init(dev ? atoi(dev) : 0, &g_shared_ctx));
+    }
+    *ctx = g_shared_ctx;
+    return CALZ_OK;
+}
+
+int calz_mat_cache_clear(calz_ctx* ctx) {
+    for (size_t i = 0; i < g_mat_cache.size();) {
+        if (!ctx || g_mat_cache[i].m->ctx == ctx) {
+            calz_mat_destroy(g_mat_cache[i].m);
+            g_mat_cache.erase(g_mat_cache.begin() + i);
+        } else {
+            ++i;
+        }
+    }
+    return CALZ_OK;
+}
+
+int calz_shared_release(void) {
+    calz_mat_cache_clear(nullptr);
+    int st = CALZ_OK;
+    if (g_shared_ctx) st = calz_finalize(g_shared_ctx);
+    g_shared_ctx = nullptr;
+    return st;
+}
+
+int calz_mat_cache_get_csc64(calz_ctx* ctx, int64_t n, const uint64_t* jc, const uint64_t* ir, const double* pr, int s_max,
+                             int layout, calz_mat** mat) {
+    if (!ctx || !jc || !ir || !pr || !mat || n <= 0) return set_error(ctx, CALZ_ERR_BADARG, "calz_mat_cache_get_csc64: bad arguments");
+    const uint64_t nnz = jc[n];
+    const uint64_t fp = csc_fingerprint(n, nnz, jc, ir, pr);
+    for (size_t i = 0; i < g_mat_cache.size(); ++i) {
+        CachedMat& c = g_mat_cache[i];
+        if (c.m->ctx != ctx || c.pr != (const void*)pr || c.n != n || c.nnz != nnz) continue;
+        if (c.fp == fp && c.s_max >= s_max && c.layout == layout) { *mat = c.m; return CALZ_OK; }
+        calz_mat_destroy(c.m);                                  // same address, different content (or too small an s_max): stale
+        g_mat_cache.erase(g_mat_cache.begin() + i);
+        break;
+    }
+    if (g_mat_cache.size() >= 4) calz_mat_cache_clear(ctx);     // small cache: drop everything when it fills up
+    calz_mat* m = nullptr;
+    CALZ_TRY(calz_mat_create_csc64(ctx, n, jc, ir, pr, s_max, layout, &m));
+    g_mat_cache.push_back(CachedMat{(const void*)pr, n, nnz, fp, s_max, layout, m});
+    *mat = m;
+    return CALZ_OK;
+}
+
+// ---- device blocks
+}  // extern "C"
+struct calz_vec {
+    calz_ctx* ctx;
+    double* d;
+    int64_t n, ld;
+    int cols;
+};
+extern "C" {
+
+int calz_vec_create(calz_ctx* ctx, int64_t n, int cols, calz_vec** out) {
+    if (!ctx || !out || n < 1 || cols < 1) return set_error(ctx, CALZ_ERR_BADARG, "calz_vec_create: bad arguments");
+    CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    calz_vec* v = new calz_vec{ctx, nullptr, n, round_up(n, 32), cols};
+    const size_t bytes = (size_t)v->ld * cols * sizeof(double);
+    cudaError_t e = cudaMalloc(&v->d, bytes);
+    if (e != cudaSuccess) {
+        delete v;
+        return set_error(ctx, CALZ_ERR_ALLOC, "calz_vec_create: cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    CALZ_CUDA(ctx, cudaMemsetAsync(v->d, 0, bytes, ctx->stream));
+    *out = v;
+    return CALZ_OK;
+}
+
+int calz_vec_destroy(calz_vec* v) {
+    if (!v) return CALZ_OK;
+    cudaStreamSynchronize(v->ctx->stream);
+    cudaFree(v->d);
+    delete v;
+    return CALZ_OK;
+}
+
+int calz_vec_info(const calz_vec* v, double** dev, int64_t* n, int* cols, int64_t* ld) {
+    if (!v) return CALZ_ERR_BADARG;
+    if (dev) *dev = v->d;
+    if (n) *n = v->n;
+    if (cols) *cols = v->cols;
+    if (ld) *ld = v->ld;
+    return CALZ_OK;
+}
+
+int calz_vec_upload(calz_vec* v, int col0, int cols, const double* host, int64_t ldh) {
+    if (!v || !host || col0 < 0 || cols < 1 || col0 + cols > v->cols || ldh < v->n)
+        return set_error(v ? v->ctx : nullptr, CALZ_ERR_BADARG, "calz_vec_upload: bad arguments");
+    calz_ctx* ctx = v->ctx;
+    CALZ_CUDA(ctx, cudaMemcpy2DAsync(v->d + (size_t)col0 * v->ld, (size_t)v->ld * sizeof(double), host, (size_t)ldh * sizeof(double),
+                                     (size_t)v->n * sizeof(double), (size_t)cols, cudaMemcpyHostToDevice, ctx->stream));
+    CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));          // the host buffer may be reused at once (MATLAB value semantics)
+    return CALZ_OK;
+}
+
+int calz_vec_download(const calz_vec* v, int col0, int cols, double* host, int64_t ldh) {
+    if (!v || !host || col0 < 0 || cols < 1 || col0 + cols > v->cols || ldh < v->n)
+        return set_error(v ? v->ctx : nullptr, CALZ_ERR_BADARG, "calz_vec_download: bad arguments");
+    calz_ctx* ctx = v->ctx;
+    CALZ_CUDA(ctx, cudaMemcpy2DAsync(host, (size_t)ldh * sizeof(double), v->d + (size_t)col0 * v->ld, (size_t)v->ld * sizeof(double),
+                                     (size_t)v->n * sizeof(double), (size_t)cols, cudaMemcpyDeviceToHost, ctx->stream));
+    CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CALZ_OK;
 }
 

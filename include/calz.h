@@ -68,6 +68,33 @@ int64_t calz_launch_count(calz_ctx* ctx, int reset);
  * "cholqr2_inv_thresh" (second pass when min_j R_jj/||x_j|| < 1/value; default 32) */
 int  calz_set_option(calz_ctx* ctx, const char* key, int64_t value);
 
+/* ------------------------------------------------------------------ process-wide state (MEX gateways) -- */
+/* The eight MEX gateways are eight shared objects in one MATLAB/Octave process.  They must share ONE context (one CUDA
+ * context's worth of scratch) and ONE device-matrix cache, so both live inside libcalz.so, which the process maps once:
+ * calz_shared_context creates the context on first use (device from CALZ_DEVICE, default 0) and returns the same one afterwards;
+ * calz_shared_release destroys the cache and the context (mexAtExit). */
+int  calz_shared_context(calz_ctx** ctx);
+int  calz_shared_release(void);
+/* Device copy of a MATLAB sparse matrix (CSC, 64-bit mwIndex: mxGetJc/mxGetIr/mxGetPr), uploaded once and reused across
+ * calls (SpMV.m:3-5 "other data structures").  Keyed on (pr, n, nnz) AND a content fingerprint -- a hash of 4096 strided
+ * samples of pr/ir/jc plus their ends -- because MATLAB reuses freed data pointers: `A = sparse(diag(a))` rebuilt in a loop
+ * with constant n (test_restart_diagonal_matrices.m:23) would otherwise hit the previous matrix.  A stale entry is replaced.
+ * calz_mat_cache_clear drops every cached matrix (explicit invalidation). */
+int  calz_mat_cache_get_csc64(calz_ctx* ctx, int64_t n, const uint64_t* jc, const uint64_t* ir, const double* pr, int s_max,
+                              int layout, calz_mat** mat);
+int  calz_mat_cache_clear(calz_ctx* ctx);
+
+/* ------------------------------------------------------------------ device blocks (handle mode) ------- */
+/* An n x cols fp64 block that lives on the device (column-major, leading dimension ld = n rounded up to 32): what a gateway
+ * hands back instead of a host array in handle mode (mex/README.md), so that V, Q and QZ never cross PCIe between calls.
+ * The device pointer feeds the un-suffixed entry points (calz_mpk_newton, calz_project_and_normalize, ...). */
+typedef struct calz_vec calz_vec;
+int  calz_vec_create(calz_ctx* ctx, int64_t n, int cols, calz_vec** v);
+int  calz_vec_destroy(calz_vec* v);
+int  calz_vec_info(const calz_vec* v, double** dev, int64_t* n, int* cols, int64_t* ld);
+int  calz_vec_upload(calz_vec* v, int col0, int cols, const double* host, int64_t ldh);        /* host -> columns [col0, col0+cols) */
+int  calz_vec_download(const calz_vec* v, int col0, int cols, double* host, int64_t ldh);      /* synchronous */
+
 /* ------------------------------------------------------------------ multi-GPU plumbing --------------- */
 /* One process per GPU.  The 128-byte id is created on rank 0 and shipped by the host framework
  * (torch.distributed broadcast); nccl_lib may be NULL (uses the libnccl.so.2 already in the process). */
