@@ -560,8 +560,50 @@ def run_e2e(args, torch, dist, ctx, dm, eng, shifts, world, dev, barrier):
     dt = float(t.item())
     h2d = 8 * n_own * (1 + (s + 1) + s) * world
     d2h = 8 * n_own * ((s + 1) + s) * world
+    # ---- PCIe floor of this call sequence: the same bytes with plain pinned copies, one direction at a time (the calls are
+    #      synchronous and each output depends on all of its inputs, so the two directions cannot overlap inside a call)
+    big = torch.empty((s + 1, n_own), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for _ in range(2):
+        big.copy_(tV, non_blocking=True); torch.cuda.synchronize(dev)
+        tV.copy_(big, non_blocking=True); torch.cuda.synchronize(dev)
+    pc = (time.perf_counter() - t0) / 4
+    h2d_gbs = 8.0 * n_own * (s + 1) / pc / 1e9
+    floor_s = (h2d / world + d2h / world) / (h2d_gbs * 1e9)
+    del big
+    # ---- the same block through the HANDLE mode of the call surface (api.DeviceBlock == mex/calz_vec.m): same public functions,
+    #      device blocks in and out, only the small R factors come back to the host
+    hv = None
+    try:
+        Qb = api.DeviceBlock(n_own, s + 1, ctx)
+        Qb[:, 0:s + 1] = Qprev
+        Vb = api.DeviceBlock(n_own, s + 1, ctx)
+        Zb = api.DeviceBlock(n_own, s, ctx)
+        ht = []
+        for i in range(steps + 2):
+            barrier()
+            t0 = time.perf_counter()
+            api.matrix_powers_newton(dm, Qb[:, s:s + 1], s, shifts, 1, out=Vb)
+            _, RZh = api.projectAndNormalize([Qb[:, 0:s + 1]], Vb[:, 1:s + 1], True, ctx=ctx, out=Zb)
+            barrier()
+            if i > 1:
+                ht.append(time.perf_counter() - t0)
+            Qb[:, 0:1] = Qb[:, s:s + 1]
+            Qb[:, 1:s + 1] = Zb
+        th = torch.tensor([float(np.mean(ht))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(th, op=dist.ReduceOp.MAX)
+        hv = {"value": 1.0 / float(th.item()), "unit": "blocks/s", "h2d_bytes_per_step": 0,
+              "d2h_bytes_per_step": int(8 * ((s + 1) * s + s * s)), "steps": steps,
+              "api": "the same two public calls with api.DeviceBlock arguments (handle mode, mex/calz_vec.m): blocks stay in HBM, "
+                     "the coefficient blocks come back to the host every call; synchronous, one call at a time"}
+    except Exception as e:                       # the value-semantics number above must not depend on this extra
+        hv = {"error": str(e)}
     return {"value": 1.0 / dt, "unit": "blocks/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": steps,
-            "api": "matrix_powers_newton + projectAndNormalize (host arrays, pinned), timed with perf_counter around barrier+sync"}
+            "api": "matrix_powers_newton + projectAndNormalize (host arrays, pinned), timed with perf_counter around barrier+sync",
+            "pcie_gbs_measured": h2d_gbs, "pcie_floor_blocks_per_s": 1.0 / floor_s, "frac_of_pcie_floor": floor_s / dt,
+            "handles": hv}
 
 
 def _dist_setup(args):

@@ -44,6 +44,7 @@ SIGNATURES = {
     "calz_vec_info": (C.c_int, [c_vp, C.POINTER(c_vp), c_i64p, c_ip, c_i64p]),
     "calz_vec_upload": (C.c_int, [c_vp, C.c_int, C.c_int, c_dp, c_i64]),
     "calz_vec_download": (C.c_int, [c_vp, C.c_int, C.c_int, c_dp, c_i64]),
+    "calz_vec_copy": (C.c_int, [c_vp, C.c_int, c_vp, C.c_int, C.c_int]),
     "calz_comm_unique_id": (C.c_int, [C.c_char_p, C.c_char_p]),
     "calz_comm_init": (C.c_int, [c_vp, C.c_int, C.c_int, C.c_char_p, C.c_char_p]),
     "calz_comm_rank": (C.c_int, [c_vp, c_ip, c_ip]),

@@ -23,7 +23,7 @@ from . import _lib
 from ._lib import CalzError, check
 
 __all__ = [
-    "Context", "DeviceMatrix", "default_context", "set_qr_backend", "get_qr_backend",
+    "Context", "DeviceMatrix", "DeviceBlock", "default_context", "set_qr_backend", "get_qr_backend",
     "SpMV", "matrix_powers_monomial", "matrix_powers_newton", "tsqr", "cholqr", "normalize", "project",
     "projectAndNormalize", "CalzError",
 ]
@@ -183,6 +183,78 @@ class DeviceMatrix:
             pass
 
 
+class DeviceBlock:
+    """n x cols fp64 block that lives on the device (calz_vec; the MATLAB side is mex/calz_vec.m): the handle mode of the call
+    surface.  ``matrix_powers_newton`` / ``matrix_powers_monomial`` / ``normalize`` / ``projectAndNormalize`` return DeviceBlocks
+    when they are given DeviceBlocks, so V, Q and QZ never cross PCIe between calls; ``B[:, a:b]`` is a zero-copy column view,
+    ``B[:, a:b] = other`` a device-to-device copy (or an upload), ``B.to_host()`` brings the block back."""
+
+    def __init__(self, n=None, cols=None, ctx: Context | None = None, _view=None):
+        self.ctx = ctx or default_context()
+        if _view is not None:
+            self.owner, self.h, self.n, self.col0, self.ncols, self.ld, self._base = _view
+            return
+        h = C.c_void_p()
+        check(self.ctx.lib.calz_vec_create(self.ctx.h, int(n), int(cols), C.byref(h)), self.ctx.h)
+        dev, nn, cc, ld = C.c_void_p(), C.c_int64(), C.c_int(), C.c_int64()
+        check(self.ctx.lib.calz_vec_info(h, C.byref(dev), C.byref(nn), C.byref(cc), C.byref(ld)), self.ctx.h)
+        self.owner, self.h, self.n, self.col0, self.ncols, self.ld, self._base = None, h, int(n), 0, int(cols), int(ld.value), int(dev.value)
+
+    @classmethod
+    def from_host(cls, X, ctx: Context | None = None):
+        X = _f64_fortran(X)
+        b = cls(X.shape[0], X.shape[1], ctx)
+        check(b.ctx.lib.calz_vec_upload(b.h, 0, X.shape[1], _dp(X), X.shape[0]), b.ctx.h)
+        return b
+
+    @property
+    def ptr(self) -> int:
+        return self._base + 8 * self.ld * self.col0
+
+    @property
+    def shape(self):
+        return (self.n, self.ncols)
+
+    def _range(self, key):
+        if not (isinstance(key, tuple) and len(key) == 2 and key[0] == slice(None)):
+            raise IndexError("DeviceBlock views are B[:, a:b]")
+        k = key[1]
+        if isinstance(k, int):
+            k = slice(k, k + 1)
+        a, b, st = k.indices(self.ncols)
+        if st != 1 or b <= a:
+            raise IndexError("DeviceBlock views are contiguous column ranges")
+        return a, b
+
+    def __getitem__(self, key):
+        a, b = self._range(key)
+        return DeviceBlock(ctx=self.ctx, _view=(self.owner or self, self.h, self.n, self.col0 + a, b - a, self.ld, self._base))
+
+    def __setitem__(self, key, value):
+        a, b = self._range(key)
+        if isinstance(value, DeviceBlock):
+            if value.shape != (self.n, b - a):
+                raise ValueError("shape mismatch")
+            check(self.ctx.lib.calz_vec_copy(self.h, self.col0 + a, value.h, value.col0, b - a), self.ctx.h)
+        else:
+            X = _f64_fortran(value)
+            if X.shape != (self.n, b - a):
+                raise ValueError("shape mismatch")
+            check(self.ctx.lib.calz_vec_upload(self.h, self.col0 + a, b - a, _dp(X), self.n), self.ctx.h)
+
+    def to_host(self, out=None):
+        X = _out_array(out, (self.n, self.ncols))
+        check(self.ctx.lib.calz_vec_download(self.h, self.col0, self.ncols, _dp(X), self.n), self.ctx.h)
+        return X
+
+    def __del__(self):
+        try:
+            if self.owner is None and getattr(self, "h", None) and getattr(self.ctx, "h", None):
+                self.ctx.lib.calz_vec_destroy(self.h)
+        except Exception:
+            pass
+
+
 # ---- device-matrix cache (the MEX gateway keys on mxGetPr(A)+n+nnz; here on the host object)
 _mat_cache: dict = {}
 
@@ -221,6 +293,12 @@ def matrix_powers_monomial(A, q, s):
     """matrix_powers_monomial.m:6-12 -- V = [A q, ..., A^s q], n x s (q itself NOT included)."""
     s = int(s)
     dm = _device_matrix(A, s)
+    if isinstance(q, DeviceBlock):                                 # handle mode: device block in, device block out
+        if q.shape != (dm.n, 1):
+            raise ValueError("matrix_powers_monomial: dimension mismatch")
+        V = DeviceBlock(dm.n, s, dm.ctx)
+        check(dm.ctx.lib.calz_mpk_monomial(dm.h, C.c_void_p(q.ptr), s, C.c_void_p(V.ptr), V.ld), dm.ctx.h)
+        return V
     q = np.ascontiguousarray(np.asarray(q, dtype=np.float64).ravel())
     if q.shape[0] != dm.n:
         raise ValueError("matrix_powers_monomial: dimension mismatch")
@@ -243,18 +321,28 @@ def matrix_powers_newton(A, v, s, lam, modifiedp=0, out=None):
     ``out`` (extension): write the result into a caller-owned array instead of a fresh one."""
     s = int(s)
     dm = _device_matrix(A, s)
-    v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).ravel())
-    if v.shape[0] != dm.n:
-        raise ValueError("matrix_powers_newton: dimension mismatch")
     lam = np.asarray(lam).ravel()
     if lam.shape[0] < s:
         raise ValueError("matrix_powers_newton: need at least s shifts")
     re = np.ascontiguousarray(np.real(lam[:s]), dtype=np.float64)
     im = np.ascontiguousarray(np.imag(lam[:s]), dtype=np.float64) if np.iscomplexobj(lam) else None
-    V = _out_array(out, (dm.n, s + 1))
+    handle = isinstance(v, DeviceBlock)
+    if handle:                                                     # handle mode: device block in, device block out
+        if v.shape != (dm.n, 1):
+            raise ValueError("matrix_powers_newton: dimension mismatch")
+        V = out if isinstance(out, DeviceBlock) else DeviceBlock(dm.n, s + 1, dm.ctx)
+    else:
+        v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).ravel())
+        if v.shape[0] != dm.n:
+            raise ValueError("matrix_powers_newton: dimension mismatch")
+        V = _out_array(out, (dm.n, s + 1))
     try:
-        check(dm.ctx.lib.calz_mpk_newton_host(dm.h, _dp(v), s, _dp(re), _dp(im) if im is not None else None,
-                                              int(modifiedp), _dp(V), dm.n), dm.ctx.h)
+        if handle:
+            check(dm.ctx.lib.calz_mpk_newton(dm.h, C.c_void_p(v.ptr), s, _dp(re), _dp(im) if im is not None else None,
+                                             int(modifiedp), C.c_void_p(V.ptr), V.ld), dm.ctx.h)
+        else:
+            check(dm.ctx.lib.calz_mpk_newton_host(dm.h, _dp(v), s, _dp(re), _dp(im) if im is not None else None,
+                                                  int(modifiedp), _dp(V), dm.n), dm.ctx.h)
     except CalzError as e:
         if e.code == 8:           # matrix_powers_newton.m:36-39 error(...)
             raise ValueError(str(e)) from None
@@ -292,10 +380,19 @@ def normalize(X, opt="None", tol=1.0e-8, backend: str | None = None, ctx: Contex
     if str(opt).lower() == "randomizenullspace":
         raise NotImplementedError("normalize(...,'randomizeNullSpace') is never requested on the hot path")
     ctx = ctx or default_context()
+    rank = C.c_int(0)
+    if isinstance(X, DeviceBlock):                                 # handle mode
+        n, c = X.shape
+        Q = DeviceBlock(n, c, X.ctx); R = np.empty((c, c), order="F")
+        st = X.ctx.lib.calz_normalize(X.ctx.h, n, c, C.c_void_p(X.ptr), X.ld, _lib.QR[backend or _QR_BACKEND], float(tol),
+                                      C.c_void_p(Q.ptr), Q.ld, _dp(R), C.byref(rank))
+        if st == _lib.ERR_CHOL:
+            raise np.linalg.LinAlgError("Matrix must be positive definite")
+        check(st, X.ctx.h)
+        return Q, R, int(rank.value)
     X = _f64_fortran(X)
     n, c = X.shape
     Q = np.empty((n, c), order="F"); R = np.empty((c, c), order="F")
-    rank = C.c_int(0)
     st = ctx.lib.calz_normalize_host(ctx.h, n, c, _dp(X), n, _lib.QR[backend or _QR_BACKEND], float(tol), _dp(Q), n,
                                      _dp(R), C.byref(rank))
     if st == _lib.ERR_CHOL:
@@ -347,6 +444,32 @@ def projectAndNormalize(Q, X, doreorth=True, backend: str | None = None, info: d
     """projectAndNormalize.m:3-90 -- returns (QZ, RZ) with RZ a list of len(Q)+1 blocks (last = R of the last
     normalize).  ``info`` receives 'second_pass' (the reference prints 'second', :62) and 'rank'."""
     ctx = ctx or default_context()
+    if isinstance(X, DeviceBlock):                                 # handle mode: device blocks in, QZ a device block (or `out`)
+        if not isinstance(Q, (list, tuple)):
+            raise TypeError("Input Q (arg 1) must be cell (block) array.")
+        n, c = X.shape
+        nb = len(Q)
+        blocks = [b if (b is not None and not (isinstance(b, np.ndarray) and b.size == 0)) else None for b in Q]
+        if any(b is not None and not isinstance(b, DeviceBlock) for b in blocks):
+            raise TypeError("projectAndNormalize: host arrays and DeviceBlocks cannot be mixed")
+        qb = (C.c_void_p * max(nb, 1))(*[(b.ptr if b is not None else None) for b in blocks])
+        lds = (C.c_int64 * max(nb, 1))(*[(b.ld if b is not None else n) for b in blocks])
+        mc = (C.c_int * max(nb, 1))(*[(b.ncols if b is not None else 0) for b in blocks])
+        R = [np.zeros((b.ncols, c), order="F") if b is not None else None for b in blocks]
+        rp = (_lib.c_dp * max(nb, 1))(*[(_dp(r) if r is not None else None) for r in R])
+        Rlast = np.zeros((c, c), order="F")
+        QZ = out if isinstance(out, DeviceBlock) else DeviceBlock(n, c, X.ctx)
+        second = C.c_int(0); rank = C.c_int(0)
+        st = X.ctx.lib.calz_project_and_normalize(X.ctx.h, n, nb, qb, lds, mc, c, C.c_void_p(X.ptr), X.ld, 1 if doreorth else 0,
+                                                  _lib.QR[backend or _QR_BACKEND], C.c_void_p(QZ.ptr), QZ.ld, rp, _dp(Rlast),
+                                                  C.byref(second), C.byref(rank))
+        if st == _lib.ERR_CHOL:
+            raise np.linalg.LinAlgError("Matrix must be positive definite")
+        check(st, X.ctx.h)
+        if info is not None:
+            info["second_pass"] = bool(second.value)
+            info["rank"] = int(rank.value)
+        return QZ, list(R) + [Rlast]
     X = _f64_fortran(X)
     n, c = X.shape
     nb, ptrs, lds, mc, keep = _cell(Q, n)

@@ -87,7 +87,9 @@ struct calz_ctx {
     int64_t opt_pan_fused_solve = 1; // tile pipeline, Cholesky back ends: downdated Gram + fused (update, triangular solve) last pass
     int64_t opt_mpk_dict_mode = -1;  // dictionary SELL: where the dictionary lives (0 shared memory, 2 constant bank, -1 by code uniformity)
     int64_t opt_mpk_halo_level = 0;  // depth of the ghost closure = MPK steps per halo exchange (0: automatic, see matrix.cu)
-    int64_t opt_mpk_fused_steps = 1; // dictionary SELL: all steps of an exchange group in one cooperative launch (grid barriers)
+    int64_t opt_mpk_patterns = 1;    // dictionary SELL: slice-pattern kernel (k_spmv_selp) when most slices have a pattern
+    int64_t opt_mpk_fused_steps = 0; // dictionary SELL: all steps of an exchange group in one cooperative launch (grid barriers); measured: no gain over
+                                     // back-to-back launches (0.848 vs 0.850 ms per C3 MPK, 0.182 vs 0.176 ms on a 2.6 M-row slab) => off
     int64_t opt_mpk_persist = 1;     // dictionary SELL: persistent, software-pipelined kernel (0 = one CTA per 16 slices)
     int64_t opt_sell_dict = 1;       // layout=auto may pick the dictionary-coded SELL variant
     int64_t opt_fused_allreduce = 1; // tile passes: the finalize launch is the peer-memory all-reduce as well

@@ -245,6 +245,7 @@ int calz_set_option(calz_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "mpk_persist")) ctx->opt_mpk_persist = value;
     else if (!strcmp(key, "mpk_halo_level")) ctx->opt_mpk_halo_level = value;
     else if (!strcmp(key, "mpk_fused_steps")) ctx->opt_mpk_fused_steps = value;
+    else if (!strcmp(key, "mpk_patterns")) ctx->opt_mpk_patterns = value;
     else if (!strcmp(key, "mpk_dict_mode")) ctx->opt_mpk_dict_mode = value;
     else if (!strcmp(key, "mpk_xs_rows")) ctx->opt_mpk_xs_rows = value;
     else if (!strcmp(key, "tile_pipeline")) ctx->opt_tile_pipeline = value;
@@ -392,6 +393,16 @@ int calz_vec_download(const calz_vec* v, int col0, int cols, double* host, int64
     CALZ_CUDA(ctx, cudaMemcpy2DAsync(host, (size_t)ldh * sizeof(double), v->d + (size_t)col0 * v->ld, (size_t)v->ld * sizeof(double),
                                      (size_t)v->n * sizeof(double), (size_t)cols, cudaMemcpyDeviceToHost, ctx->stream));
     CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CALZ_OK;
+}
+
+int calz_vec_copy(calz_vec* dst, int dcol0, const calz_vec* src, int scol0, int cols) {
+    if (!dst || !src || dst->n != src->n || cols < 1 || dcol0 < 0 || scol0 < 0 || dcol0 + cols > dst->cols || scol0 + cols > src->cols)
+        return set_error(dst ? dst->ctx : nullptr, CALZ_ERR_BADARG, "calz_vec_copy: bad arguments");
+    calz_ctx* ctx = dst->ctx;
+    CALZ_CUDA(ctx, cudaMemcpy2DAsync(dst->d + (size_t)dcol0 * dst->ld, (size_t)dst->ld * sizeof(double), src->d + (size_t)scol0 * src->ld,
+                                     (size_t)src->ld * sizeof(double), (size_t)src->n * sizeof(double), (size_t)cols,
+                                     cudaMemcpyDeviceToDevice, ctx->stream));
     return CALZ_OK;
 }
 

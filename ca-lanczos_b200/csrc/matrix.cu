@@ -104,7 +104,7 @@ int calz_mat_destroy(calz_mat* m) {
     if (!m) return CALZ_OK;
     if (m->ctx) cudaStreamSynchronize(m->ctx->stream);
     p2p_halo_teardown(m);
-    void* ptrs[] = {m->d_gridbar, m->d_long_row, m->d_long_seg0, m->d_long_segptr, m->d_long_segrow, m->d_long_col, m->d_long_val, m->d_long_part,
+    void* ptrs[] = {m->d_slice_pat, m->d_gridbar, m->d_long_row, m->d_long_seg0, m->d_long_segptr, m->d_long_segrow, m->d_long_col, m->d_long_val, m->d_long_part,
                     m->d_xs_off, m->d_codes, m->d_dict, m->d_send_idx, m->d_send_buf, m->d_rowptr, m->d_colind, m->d_val, m->d_slice_ptr,
                     m->d_sell_col, m->d_sell_val, m->d_perm, m->d_W_alloc};
     for (void* p : ptrs)
@@ -509,6 +509,84 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
             m->h_dict->e[k].v = dict_val[k];
             m->h_dict->e[k].offb = (int)(o * 8);
         }
+        // ---- slice patterns (see matrix.h): one-block slices of 32 complete rows whose lanes agree on the value of every offset
+        {
+            std::vector<uint8_t> spat((size_t)m->sell_slices + 4, (uint8_t)255);
+            std::map<std::vector<uint64_t>, int> pat_lut;
+            int64_t covered = 0;
+            for (int64_t sl = 0; sl < m->sell_slices; ++sl) {
+                if (slice_ptr[sl + 1] - slice_ptr[sl] > 1 || (sl + 1) * C > n_loc) continue;
+                if (slice_ptr[sl + 1] == slice_ptr[sl]) {            // 32 empty rows (level-L ghosts): the empty pattern
+                    std::vector<uint64_t> key;
+                    auto it = pat_lut.find(key);
+                    if (it == pat_lut.end()) {
+                        if (pat_lut.size() >= 32) continue;
+                        it = pat_lut.emplace(key, (int)pat_lut.size()).first;
+                    }
+                    spat[sl] = (uint8_t)it->second;
+                    ++covered;
+                    continue;
+                }
+                const uint8_t* pb = packed.data() + (size_t)slice_ptr[sl] * 256;
+                int32_t offs[8]; uint64_t vbits[8]; uint32_t masks[8];
+                int cnt = 0;
+                bool ok = true;
+                for (int lane = 0; lane < 32 && ok; ++lane)
+                    for (int q = 0; q < 8 && ok; ++q) {
+                        const uint8_t cd = pb[lane * 8 + q];
+                        if (cd == 255) continue;
+                        const int32_t o = dict_off[cd];
+                        uint64_t vb;
+                        memcpy(&vb, &dict_val[cd], 8);
+                        int k = 0;
+                        while (k < cnt && offs[k] != o) ++k;
+                        if (k == cnt) {
+                            if (cnt == 8) { ok = false; break; }
+                            offs[cnt] = o; vbits[cnt] = vb; masks[cnt] = 0; ++cnt;
+                        } else if (vbits[k] != vb) { ok = false; break; }
+                        if (masks[k] & (1u << lane)) { ok = false; break; }          // the same offset twice in one row
+                        masks[k] |= 1u << lane;
+                    }
+                if (!ok) continue;
+                // ascending offset = ascending column = the CSR order of every row
+                int ord[8];
+                for (int k = 0; k < cnt; ++k) ord[k] = k;
+                std::sort(ord, ord + cnt, [&](int a, int b) { return offs[a] < offs[b]; });
+                std::vector<uint64_t> key;
+                for (int k = 0; k < cnt; ++k) { key.push_back((uint64_t)(uint32_t)offs[ord[k]]); key.push_back(vbits[ord[k]]); key.push_back(masks[ord[k]]); }
+                auto it = pat_lut.find(key);
+                if (it == pat_lut.end()) {
+                    if (pat_lut.size() >= 32) continue;
+                    it = pat_lut.emplace(key, (int)pat_lut.size()).first;
+                    for (int k = 0; k < cnt; ++k) {
+                        auto& e = m->h_pat->e[it->second][k];
+                        memcpy(&e.v, &vbits[ord[k]], 8);
+                        e.offb = offs[ord[k]] * 8;
+                        e.mask = masks[ord[k]];
+                    }
+                }
+                spat[sl] = (uint8_t)it->second;
+                ++covered;
+            }
+            // most frequent pattern first: the kernel keeps pattern 0 in registers
+            const int np = (int)pat_lut.size();
+            std::vector<int64_t> freq(np, 0);
+            for (int64_t sl = 0; sl < m->sell_slices; ++sl)
+                if (spat[sl] != 255) freq[spat[sl]]++;
+            std::vector<int> order(np), newid(np);
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return freq[a] > freq[b]; });
+            auto old = *m->h_pat;
+            for (int k = 0; k < np; ++k) {
+                newid[order[k]] = k;
+                for (int q = 0; q < 8; ++q) m->h_pat->e[k][q] = old.e[order[k]][q];
+            }
+            for (int64_t sl = 0; sl < m->sell_slices; ++sl)
+                if (spat[sl] != 255) spat[sl] = (uint8_t)newid[spat[sl]];
+            m->n_pat = np;
+            m->pat_cover = m->sell_slices ? (double)covered / (double)m->sell_slices : 0.0;
+            CALZ_TRY(upload(ctx, &m->d_slice_pat, spat));
+        }
         m->sell_padded = blocks * 256;
         m->dict_size = (int)dict_val.size();
         CALZ_TRY(upload(ctx, &m->d_slice_ptr, slice_ptr));
@@ -663,6 +741,8 @@ int calz_mat_info(const calz_mat* m, const char* what, int64_t* value) {
     else if (!strcmp(what, "ldW")) *value = m->ldW;
     else if (!strcmp(what, "dict_size")) *value = m->dict_size;
     else if (!strcmp(what, "dict_uniform_pct")) *value = (int64_t)(100.0 * m->dict_uniform);
+    else if (!strcmp(what, "n_patterns")) *value = m->n_pat;
+    else if (!strcmp(what, "pattern_cover_pct")) *value = (int64_t)(100.0 * m->pat_cover);
     else if (!strcmp(what, "xs_rows")) *value = m->xs_rows;
     else if (!strcmp(what, "xs_groups")) *value = m->xs_groups;
     else if (!strcmp(what, "p2p_halo")) *value = m->p2p_halo ? 1 : 0;

@@ -64,6 +64,14 @@ struct calz_mat {
     double dict_uniform = 0.0;                        // fraction of (block, slot) positions whose 32 lanes share one code
     struct alignas(16) HostDictEnt { double v; int offb; int pad; };
     struct { HostDictEnt e[256]; } h_dict[1] = {};       // host copy, passed to the kernels as a constant-bank parameter
+    // slice patterns: a slice whose 32 rows hold the SAME (offset, value) entries -- possibly on a subset of the lanes, e.g. the
+    // x-boundary rows of a stencil miss one neighbour -- is described by one of <= 32 patterns of <= 8 {value, byte offset, lane
+    // mask} entries instead of 256 code bytes: the kernel then neither reads codes nor decodes them (mpk.cu, k_spmv_selp)
+    struct alignas(16) HostPatEnt { double v; int offb; unsigned mask; };
+    struct { HostPatEnt e[32][8]; } h_pat[1] = {};
+    int n_pat = 0;
+    double pat_cover = 0.0;                           // fraction of the slices that have a pattern
+    uint8_t* d_slice_pat = nullptr;                   // per slice: pattern number, 255 = none (coded path)
     // ... and its TMA-staged kernel: x segments of a CTA's row block (merged over overlapping offsets)
     int xs_rows = 0;                                  // rows per CTA (0: staged kernel not applicable)
     int xs_groups = 0;

@@ -314,11 +314,8 @@ static int pan_enqueue(calz_ctx* ctx, int64_t n, int nblk, const double* const* 
     // fused tile pipeline (tiles.cu): one previous block, Cholesky-based QR, TMA-compatible alignment
     const bool tile_shape = nb == 1 && fuse_norms && ctx->opt_tile_pipeline && mcols[blocks[0]] <= 16 && c <= 16;   // same on all ranks
     const bool tiled = tile_shape && tile_path_ok(n, Qblk[blocks[0]], ldQ[blocks[0]], mcols[blocks[0]], X, ldX, c, QZ, ldQZ);
-    if (ctx->nranks > 1 && tile_shape && !tiled)
-        // alignment and the local row count differ from rank to rank; a rank that silently fell back to the generic kernels would
-        // issue a different sequence of collectives than its peers
-        return set_error(ctx, CALZ_ERR_UNSUPPORTED, "multi-rank projectAndNormalize: every rank needs >= 128 local rows and 16-byte "
-                         "aligned blocks with even leading dimensions (all ranks must take the same kernel path)");
+    // tile_path_ok depends on the block shape only (rank-local alignment / row count are handled inside the kernels), so every
+    // rank takes the same kernel path and issues the same sequence of collectives
     const bool fused_solve = tiled && backend != CALZ_QR_TSQR && ctx->opt_pan_fused_solve;
     size_t doubles = 8;                                // flags
     std::vector<size_t> off1(nb), off2(nb);

@@ -69,6 +69,7 @@ struct TileArgs {
     double* S; int ldS;                             // result: rows [0,M) = Q-part, rows [M, M+c) = block-part  (x c columns)
     double* partials; unsigned int* ticket;
     const int* pred; int want;
+    int use_tma;                                    // 0: operands not 16-byte aligned on this rank -> plain loads (same arithmetic)
 };
 
 // dynamic shared memory layout: [stages][slots][kPitch] doubles | Cs[M][8*CT] | red | barriers
@@ -136,7 +137,7 @@ k_tile(TileArgs p, int stages) {
             double* dst = tiles + (size_t)s * stage_doubles;
             const long long r0 = t * kTileRows;
             const int valid = (int)min((long long)kTileRows, p.n - r0);
-            if (valid == kTileRows) {
+            if (valid == kTileRows && p.use_tma) {
                 if (lane == 0) mbar_expect_tx(&full[s], (uint32_t)((p.M + p.c) * kTileRows * sizeof(double)));
                 __syncwarp();
                 for (int col = lane; col < p.M + p.c; col += 32) {
@@ -146,7 +147,7 @@ k_tile(TileArgs p, int stages) {
                     tma_bulk_g2s(dst + (size_t)slot * kPitch, src, kTileRows * sizeof(double), &full[s]);
                 }
             } else {
-                // ragged last tile: plain loads, zero fill, then a plain arrive
+                // ragged last tile (or operands that are not 16-byte aligned): plain loads, zero fill, then a plain arrive
                 for (int e = lane; e < (p.M + p.c) * kTileRows; e += 32) {
                     const int col = e / kTileRows, r = e % kTileRows;
                     const bool isq = col < p.M;
@@ -464,9 +465,14 @@ bool aligned16(const void* p, long long ld) { return ((uintptr_t)p % 16 == 0) &&
 
 }  // namespace
 
+// The fused passes apply to any row count and any alignment (a rank whose blocks are not 16-byte aligned, or shorter than one
+// tile, stages its tiles with plain loads instead of TMA bulk copies): which kernels run -- and therefore which collectives are
+// issued -- depends on the block SHAPE only, never on rank-local properties.
 bool tile_path_ok(int64_t n, const double* Q, int64_t ldQ, int M, const double* X, int64_t ldX, int c, const double* Y, int64_t ldY) {
-    return n >= kTileRows && M >= 1 && M <= 16 && c >= 1 && c <= 16 && aligned16(Q, ldQ) && aligned16(X, ldX) && (!Y || aligned16(Y, ldY));
+    (void)Q; (void)ldQ; (void)X; (void)ldX; (void)Y; (void)ldY;
+    return n >= 1 && M >= 1 && M <= 16 && c >= 1 && c <= 16;
 }
+static int tile_use_tma(const TileArgs& a) { return aligned16(a.Q, a.ldQ) && aligned16(a.X, a.ldX) ? 1 : 0; }
 
 // mode: 0 = COEFF (S = [Q X]'X), 1 = UPDATE_FULL (Y = X - Q*C, S = [Q Y]'Y), 2 = UPDATE_GRAM (Y = X - Q*C, S rows [M,M+c) = Y'Y)
 int tile_pass(calz_ctx* ctx, int mode, int64_t n, const double* Q, int64_t ldQ, int M, const double* X, int64_t ldX, int c,
@@ -474,6 +480,7 @@ int tile_pass(calz_ctx* ctx, int mode, int64_t n, const double* Q, int64_t ldQ, 
     TileArgs a{};
     a.n = n; a.Q = Q; a.ldQ = ldQ; a.M = M; a.X = X; a.ldX = ldX; a.c = c; a.Y = Y; a.ldY = ldY; a.C = C_dev; a.ldC = ldC;
     a.S = S_dev; a.ldS = ldS; a.pred = pred; a.want = want;
+    a.use_tma = tile_use_tma(a);
     const int MT = (M + 7) / 8, CT = (c + 7) / 8;
     int st;
     // with a communicator and the peer-memory mailbox available the finalize launch is the all-reduce too.  Not for a predicated
@@ -509,6 +516,7 @@ int tile_update_solve(calz_ctx* ctx, int64_t n, const double* Q, int64_t ldQ, in
     TileArgs a{};
     a.n = n; a.Q = Q; a.ldQ = ldQ; a.M = M; a.X = X; a.ldX = ldX; a.c = c; a.Y = QZ; a.ldY = ldQZ; a.C = C1_dev; a.ldC = ldC1;
     a.C2 = C2_dev; a.ldC2 = ldC2; a.flag2 = flag2; a.R = R_dev;
+    a.use_tma = tile_use_tma(a);
     const int MT = (M + 7) / 8, CT = (c + 7) / 8;
     if (MT == 1 && CT == 1) return launch_tile<1, 1, MODE_UPDATE_SOLVE>(ctx, a);
     if (MT == 2 && CT == 1) return launch_tile<2, 1, MODE_UPDATE_SOLVE>(ctx, a);

@@ -94,6 +94,8 @@ int  calz_vec_destroy(calz_vec* v);
 int  calz_vec_info(const calz_vec* v, double** dev, int64_t* n, int* cols, int64_t* ld);
 int  calz_vec_upload(calz_vec* v, int col0, int cols, const double* host, int64_t ldh);        /* host -> columns [col0, col0+cols) */
 int  calz_vec_download(const calz_vec* v, int col0, int cols, double* host, int64_t ldh);      /* synchronous */
+/* dst(:, dcol0 : dcol0+cols) = src(:, scol0 : scol0+cols) on the device (MATLAB `Q(:,a:b) = Q_` on handles) */
+int  calz_vec_copy(calz_vec* dst, int dcol0, const calz_vec* src, int scol0, int cols);
 
 /* ------------------------------------------------------------------ multi-GPU plumbing --------------- */
 /* One process per GPU.  The 128-byte id is created on rank 0 and shipped by the host framework

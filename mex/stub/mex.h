@@ -10,6 +10,7 @@ typedef struct mxArray_tag mxArray;
 typedef size_t mwSize;
 typedef size_t mwIndex;
 typedef enum { mxREAL = 0, mxCOMPLEX = 1 } mxComplexity;
+typedef enum { mxDOUBLE_CLASS = 6, mxUINT64_CLASS = 13 } mxClassID;
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -29,6 +30,11 @@ bool mxIsEmpty(const mxArray*);
 bool mxIsChar(const mxArray*);
 bool mxIsLogicalScalarTrue(const mxArray*);
 mxArray* mxGetCell(const mxArray*, mwIndex);
+bool mxIsClass(const mxArray*, const char*);
+mxArray* mxGetProperty(const mxArray*, mwIndex, const char*);
+void* mxGetData(const mxArray*);
+mxArray* mxCreateNumericMatrix(mwSize, mwSize, mxClassID, mxComplexity);
+int mexCallMATLAB(int, mxArray**, int, mxArray**, const char*);
 mxArray* mxCreateDoubleMatrix(mwSize, mwSize, mxComplexity);
 mxArray* mxCreateDoubleScalar(double);
 mxArray* mxCreateCellMatrix(mwSize, mwSize);

@@ -334,3 +334,56 @@ def test_restarted_ca_lanczos_on_the_c4_matrix_class():
     assert eg[4][-1] < max(10 * eo[4][-1], 1e-12)
     Q = eg[1]
     assert np.linalg.norm(Q.T @ Q - np.eye(Q.shape[1])) < 1e-10
+
+
+def test_handle_mode_call_surface_matches_host_mode():
+    """The calz_vec / DeviceBlock handle mode of the call surface (what mex/calz_vec.m + the gateways do): device blocks in, device
+    blocks out, column views, block assignment -- bit-identical to the host-array mode, and the matrix cache notices a rebuilt
+    matrix at a reused address (fingerprinted key)."""
+    A = gallery.laplace3d(20, 18, 16)
+    n, s = A.shape[0], 4
+    lam = np.array([11.0, 1.0, 6.5, 3.0])
+    v = np.cos(0.3 * np.arange(n)) + 2.0
+    v /= np.linalg.norm(v)
+    api.set_qr_backend("tsqr")
+    dm = api.DeviceMatrix(A, s_max=s)
+    Vh = api.matrix_powers_newton(dm, v, s, lam, 1)
+    Q1h, R1h, _ = api.normalize(Vh)
+    V2h = api.matrix_powers_newton(dm, Q1h[:, s], s, lam, 1)
+    QZh, RZh = api.projectAndNormalize([Q1h], V2h[:, 1:], True)
+    # the same through handles
+    vd = api.DeviceBlock.from_host(v)
+    Vd = api.matrix_powers_newton(dm, vd, s, lam, 1)
+    assert isinstance(Vd, api.DeviceBlock) and Vd.shape == (n, s + 1)
+    np.testing.assert_array_equal(Vd.to_host(), Vh)
+    Qbig = api.DeviceBlock(n, 2 * s + 1)
+    Q1d, R1d, _ = api.normalize(Vd)
+    Qbig[:, 0:s + 1] = Q1d                                         # Q(:,1:s+1) = Q_  (device-to-device)
+    np.testing.assert_array_equal(R1d, R1h)
+    V2d = api.matrix_powers_newton(dm, Qbig[:, s:s + 1], s, lam, 1)
+    QZd, RZd = api.projectAndNormalize([Qbig[:, 0:s + 1]], V2d[:, 1:s + 1], True, out=Qbig[:, s + 1:2 * s + 1])
+    np.testing.assert_array_equal(Qbig[:, s + 1:2 * s + 1].to_host(), QZh)
+    for a, b in zip(RZd, RZh):
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(api.matrix_powers_monomial(dm, vd, 3).to_host(), api.matrix_powers_monomial(dm, v, 3))
+    # fingerprinted matrix cache: same buffers, new values => a new device matrix
+    import ctypes as C
+    from ca_lanczos_b200 import _lib
+    import scipy.sparse as sp
+    ctx = api.default_context()
+    Ac = sp.csc_matrix(A).astype(np.float64)
+    jc = np.ascontiguousarray(Ac.indptr, dtype=np.uint64); ir = np.ascontiguousarray(Ac.indices, dtype=np.uint64)
+    pr = np.ascontiguousarray(Ac.data)
+    u64p = C.POINTER(C.c_uint64)
+    h1, h2, h3 = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    args = (ctx.h, n, jc.ctypes.data_as(u64p), ir.ctypes.data_as(u64p), pr.ctypes.data_as(_lib.c_dp), 8, 0)
+    _lib.check(ctx.lib.calz_mat_cache_get_csc64(*args, C.byref(h1)), ctx.h)
+    _lib.check(ctx.lib.calz_mat_cache_get_csc64(*args, C.byref(h2)), ctx.h)
+    assert h1.value == h2.value                                    # hit
+    y1 = np.empty(n); y2 = np.empty(n)
+    _lib.check(ctx.lib.calz_spmv_host(h1, v.ctypes.data_as(_lib.c_dp), y1.ctypes.data_as(_lib.c_dp)), ctx.h)
+    pr *= 2.0                                                      # "A = sparse(...)" rebuilt in place: same pointer, n, nnz
+    _lib.check(ctx.lib.calz_mat_cache_get_csc64(*args, C.byref(h3)), ctx.h)
+    _lib.check(ctx.lib.calz_spmv_host(h3, v.ctypes.data_as(_lib.c_dp), y2.ctypes.data_as(_lib.c_dp)), ctx.h)
+    np.testing.assert_allclose(y2, 2.0 * y1, rtol=1e-15)
+    ctx.lib.calz_mat_cache_clear(ctx.h)

@@ -166,16 +166,31 @@ def test_dictionary_kernel_variants_are_bit_identical(name):
     uni = dm.info("dict_uniform_pct")
     assert 0 <= uni <= 100 and (name == "lap3d" or uni < 50)     # short grid lines: partly uniform; ragged: not at all
     try:
-        for dmode in (-1, 0, 2):
-            for persist in (1, 0):
-                ctx.set_option("mpk_dict_mode", dmode)
-                ctx.set_option("mpk_persist", persist)
-                np.testing.assert_array_equal(api.matrix_powers_newton(dm, v, 4, lam, 1), ref[0])
-                np.testing.assert_array_equal(api.matrix_powers_monomial(dm, v, 3), ref[1])
+        for patterns, fused in ((1, 0), (0, 0), (0, 1)):          # slice-pattern kernel / coded kernels / one cooperative launch
+            for dmode in (-1, 0, 2):
+                for persist in (1, 0):
+                    ctx.set_option("mpk_patterns", patterns)
+                    ctx.set_option("mpk_fused_steps", fused)
+                    ctx.set_option("mpk_dict_mode", dmode)
+                    ctx.set_option("mpk_persist", persist)
+                    np.testing.assert_array_equal(api.matrix_powers_newton(dm, v, 4, lam, 1), ref[0])
+                    np.testing.assert_array_equal(api.matrix_powers_monomial(dm, v, 3), ref[1])
     finally:
         ctx.set_option("mpk_dict_mode", -1)
         ctx.set_option("mpk_persist", 1)
+        ctx.set_option("mpk_patterns", 1)
+        ctx.set_option("mpk_fused_steps", 0)
         dm.close()
+
+
+def test_slice_patterns_of_a_stencil():
+    """7-point Laplacian 64 x 40 x 33: 2 slices per grid line, the line ends miss one neighbour on one lane (lane masks); the three
+    boundary states of y and z give 27 patterns at most and every complete slice has one; pattern 0 is the interior."""
+    A = gallery.laplace3d(64, 40, 33)
+    dm = api.DeviceMatrix(A, 4, "selld")
+    assert 1 <= dm.info("n_patterns") <= 32
+    assert dm.info("pattern_cover_pct") >= 99
+    dm.close()
 
 
 @pytest.mark.parametrize("name", ["poisson100", "lap3d"])
