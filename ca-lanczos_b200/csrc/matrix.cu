@@ -512,78 +512,89 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
         // ---- slice patterns (see matrix.h): one-block slices of 32 complete rows whose lanes agree on the value of every offset
         {
             std::vector<uint8_t> spat((size_t)m->sell_slices + 4, (uint8_t)255);
+            struct Pat { int cnt; int32_t off[8]; uint64_t vb[8]; uint32_t mask[8]; int64_t freq; };
+            std::vector<Pat> pats;
             std::map<std::vector<uint64_t>, int> pat_lut;
-            int64_t covered = 0;
+            std::vector<int32_t> prov((size_t)m->sell_slices, -1);                 // provisional pattern number per slice
             for (int64_t sl = 0; sl < m->sell_slices; ++sl) {
                 if (slice_ptr[sl + 1] - slice_ptr[sl] > 1 || (sl + 1) * C > n_loc) continue;
-                if (slice_ptr[sl + 1] == slice_ptr[sl]) {            // 32 empty rows (level-L ghosts): the empty pattern
-                    std::vector<uint64_t> key;
-                    auto it = pat_lut.find(key);
-                    if (it == pat_lut.end()) {
-                        if (pat_lut.size() >= 32) continue;
-                        it = pat_lut.emplace(key, (int)pat_lut.size()).first;
-                    }
-                    spat[sl] = (uint8_t)it->second;
-                    ++covered;
-                    continue;
-                }
-                const uint8_t* pb = packed.data() + (size_t)slice_ptr[sl] * 256;
-                int32_t offs[8]; uint64_t vbits[8]; uint32_t masks[8];
-                int cnt = 0;
+                Pat P{};
                 bool ok = true;
-                for (int lane = 0; lane < 32 && ok; ++lane)
-                    for (int q = 0; q < 8 && ok; ++q) {
-                        const uint8_t cd = pb[lane * 8 + q];
-                        if (cd == 255) continue;
-                        const int32_t o = dict_off[cd];
-                        uint64_t vb;
-                        memcpy(&vb, &dict_val[cd], 8);
-                        int k = 0;
-                        while (k < cnt && offs[k] != o) ++k;
-                        if (k == cnt) {
-                            if (cnt == 8) { ok = false; break; }
-                            offs[cnt] = o; vbits[cnt] = vb; masks[cnt] = 0; ++cnt;
-                        } else if (vbits[k] != vb) { ok = false; break; }
-                        if (masks[k] & (1u << lane)) { ok = false; break; }          // the same offset twice in one row
-                        masks[k] |= 1u << lane;
-                    }
+                if (slice_ptr[sl + 1] > slice_ptr[sl]) {
+                    const uint8_t* pb = packed.data() + (size_t)slice_ptr[sl] * 256;
+                    for (int lane = 0; lane < 32 && ok; ++lane)
+                        for (int q = 0; q < 8 && ok; ++q) {
+                            const uint8_t cd = pb[lane * 8 + q];
+                            if (cd == 255) continue;
+                            const int32_t o = dict_off[cd];
+                            uint64_t vb;
+                            memcpy(&vb, &dict_val[cd], 8);
+                            int k = 0;
+                            while (k < P.cnt && P.off[k] != o) ++k;
+                            if (k == P.cnt) {
+                                if (P.cnt == 8) { ok = false; break; }
+                                P.off[k] = o; P.vb[k] = vb; P.mask[k] = 0; ++P.cnt;
+                            } else if (P.vb[k] != vb) { ok = false; break; }
+                            if (P.mask[k] & (1u << lane)) { ok = false; break; }      // the same offset twice in one row
+                            P.mask[k] |= 1u << lane;
+                        }
+                }                                                                      // else: 32 empty rows, the empty pattern
                 if (!ok) continue;
-                // ascending offset = ascending column = the CSR order of every row
-                int ord[8];
-                for (int k = 0; k < cnt; ++k) ord[k] = k;
-                std::sort(ord, ord + cnt, [&](int a, int b) { return offs[a] < offs[b]; });
                 std::vector<uint64_t> key;
-                for (int k = 0; k < cnt; ++k) { key.push_back((uint64_t)(uint32_t)offs[ord[k]]); key.push_back(vbits[ord[k]]); key.push_back(masks[ord[k]]); }
+                for (int k = 0; k < P.cnt; ++k) { key.push_back((uint64_t)(uint32_t)P.off[k]); key.push_back(P.vb[k]); key.push_back(P.mask[k]); }
+                std::sort(key.begin(), key.end());      // (order-insensitive key; entries are re-sorted by offset below)
                 auto it = pat_lut.find(key);
                 if (it == pat_lut.end()) {
-                    if (pat_lut.size() >= 32) continue;
-                    it = pat_lut.emplace(key, (int)pat_lut.size()).first;
-                    for (int k = 0; k < cnt; ++k) {
-                        auto& e = m->h_pat->e[it->second][k];
-                        memcpy(&e.v, &vbits[ord[k]], 8);
-                        e.offb = offs[ord[k]] * 8;
-                        e.mask = masks[ord[k]];
-                    }
+                    if (pats.size() >= 4096) continue;
+                    it = pat_lut.emplace(key, (int)pats.size()).first;
+                    pats.push_back(P);
                 }
-                spat[sl] = (uint8_t)it->second;
-                ++covered;
+                pats[it->second].freq++;
+                prov[sl] = it->second;
             }
-            // most frequent pattern first: the kernel keeps pattern 0 in registers
-            const int np = (int)pat_lut.size();
-            std::vector<int64_t> freq(np, 0);
-            for (int64_t sl = 0; sl < m->sell_slices; ++sl)
-                if (spat[sl] != 255) freq[spat[sl]]++;
-            std::vector<int> order(np), newid(np);
-            std::iota(order.begin(), order.end(), 0);
-            std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return freq[a] > freq[b]; });
-            auto old = *m->h_pat;
-            for (int k = 0; k < np; ++k) {
-                newid[order[k]] = k;
-                for (int q = 0; q < 8; ++q) m->h_pat->e[k][q] = old.e[order[k]][q];
+            // pattern 0 = the most frequent one, entries in ascending offset order (= ascending column = the CSR order of every
+            // row); every other pattern must be a sub-pattern of it
+            int64_t covered = 0;
+            m->n_pat = 0;
+            if (!pats.empty()) {
+                int top = 0;
+                for (size_t q = 1; q < pats.size(); ++q)
+                    if (pats[q].freq > pats[top].freq) top = (int)q;
+                const Pat& P0 = pats[top];
+                int ord[8];
+                for (int k = 0; k < P0.cnt; ++k) ord[k] = k;
+                std::sort(ord, ord + P0.cnt, [&](int a, int b) { return P0.off[a] < P0.off[b]; });
+                for (int k = 0; k < P0.cnt; ++k) {
+                    memcpy(&m->h_pat->e0[k].v, &P0.vb[ord[k]], 8);
+                    m->h_pat->e0[k].offb = P0.off[ord[k]] * 8;
+                    m->h_pat->e0[k].mask = 0xffffffffu;
+                }
+                std::vector<int> newid(pats.size(), -1);
+                auto assign = [&](int q) -> bool {                      // masks of pattern q on the entries of pattern 0
+                    if (m->n_pat >= 32) return false;
+                    unsigned mk[8] = {};
+                    for (int a = 0; a < pats[q].cnt; ++a) {
+                        int k = 0;
+                        while (k < P0.cnt && !(P0.off[ord[k]] == pats[q].off[a] && P0.vb[ord[k]] == pats[q].vb[a])) ++k;
+                        if (k == P0.cnt) return false;
+                        mk[k] = pats[q].mask[a];
+                    }
+                    for (int k = 0; k < 8; ++k) m->h_pat->mask[m->n_pat][k] = mk[k];
+                    newid[q] = m->n_pat++;
+                    return true;
+                };
+                assign(top);
+                bool full = P0.cnt >= 1;
+                for (int k = 0; k < P0.cnt; ++k) full &= P0.mask[k] == 0xffffffffu;
+                m->pat_cnt0 = full ? P0.cnt : 0;
+                std::vector<int> byfreq(pats.size());
+                std::iota(byfreq.begin(), byfreq.end(), 0);
+                std::stable_sort(byfreq.begin(), byfreq.end(), [&](int a, int b) { return pats[a].freq > pats[b].freq; });
+                for (int q : byfreq)
+                    if (q != top) assign(q);
+                for (int64_t sl = 0; sl < m->sell_slices; ++sl)
+                    if (prov[sl] >= 0 && newid[prov[sl]] >= 0) { spat[sl] = (uint8_t)newid[prov[sl]]; ++covered; }
             }
-            for (int64_t sl = 0; sl < m->sell_slices; ++sl)
-                if (spat[sl] != 255) spat[sl] = (uint8_t)newid[spat[sl]];
-            m->n_pat = np;
             m->pat_cover = m->sell_slices ? (double)covered / (double)m->sell_slices : 0.0;
             CALZ_TRY(upload(ctx, &m->d_slice_pat, spat));
         }

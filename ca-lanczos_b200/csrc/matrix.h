@@ -68,8 +68,12 @@ struct calz_mat {
     // x-boundary rows of a stencil miss one neighbour -- is described by one of <= 32 patterns of <= 8 {value, byte offset, lane
     // mask} entries instead of 256 code bytes: the kernel then neither reads codes nor decodes them (mpk.cu, k_spmv_selp)
     struct alignas(16) HostPatEnt { double v; int offb; unsigned mask; };
-    struct { HostPatEnt e[32][8]; } h_pat[1] = {};
+    // kernel parameter block: the entries of pattern 0 (the most frequent one: the interior of a stencil) and, for every pattern,
+    // one lane mask per entry of pattern 0 -- a pattern must be a sub-pattern of pattern 0 (same offsets and values on fewer
+    // lanes: boundary rows), otherwise its slices take the coded path
+    struct { HostPatEnt e0[8]; unsigned mask[32][8]; } h_pat[1] = {};
     int n_pat = 0;
+    int pat_cnt0 = 0;                                 // entries of pattern 0; 0: no usable pattern 0 (it must cover all 32 lanes)
     double pat_cover = 0.0;                           // fraction of the slices that have a pattern
     uint8_t* d_slice_pat = nullptr;                   // per slice: pattern number, 255 = none (coded path)
     // ... and its TMA-staged kernel: x segments of a CTA's row block (merged over overlapping offsets)

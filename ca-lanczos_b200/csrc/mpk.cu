@@ -222,89 +222,129 @@ struct __align__(16) PatEnt {
     int offb;
     unsigned mask;
 };
-struct PatParam {
-    PatEnt e[32][8];
+struct PatParam {                          // = calz_mat::h_pat
+    PatEnt e0[8];                          // entries of pattern 0 (ascending offset)
+    unsigned mask[32][8];                  // pattern p: lanes that hold entry k
 };
 
-template <bool NEWTON>
-__global__ void __launch_bounds__(kSpmvThreads, 4)
+// NS = 2 consecutive slices per warp and iteration (14 independent gathers in flight for a 7-point stencil).  CNT = number of
+// entries of pattern 0 (compile time: the unrolled loops carry no count tests; values and byte offsets are constant-bank operands
+// of the DFMA / address instructions).  The host only selects this kernel when pattern 0 holds every entry on every lane.
+template <bool NEWTON, int CNT>
+__global__ void __launch_bounds__(kSpmvThreads, 5)
 k_spmv_selp(const uint8_t* __restrict__ spat, const int32_t* __restrict__ slice_ptr, const uint2* __restrict__ codes,
             const __grid_constant__ DictParam D, const __grid_constant__ PatParam PP, const double* __restrict__ x,
-            const double* __restrict__ xprev, double* __restrict__ y, int slice_lo, int slice_hi, int n_loc, double shift, double pair) {
+            const double* __restrict__ xprev, double* __restrict__ y, int slice_lo, int slice_hi, int n_loc, double shift, double pair,
+            int prefetch) {
     const int lane = threadIdx.x & 31;
-    const int nsl = slice_hi - slice_lo;
+    const unsigned lanebit = 1u << lane;
+    const int items = (slice_hi - slice_lo + 1) / 2;
     const int stride = (int)gridDim.x * (kSpmvThreads / 32);
     int it = (int)blockIdx.x * (kSpmvThreads / 32) + (threadIdx.x >> 5);
-    // pattern 0 in registers (register path only if every entry covers all 32 lanes)
-    double v0[8];
-    int o0[8];
-    bool fast0 = true;
-    int cnt0 = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        v0[k] = PP.e[0][k].v;
-        o0[k] = PP.e[0][k].offb;
-        const unsigned mk = PP.e[0][k].mask;
-        if (mk != 0u && mk != 0xffffffffu) fast0 = false;
-        if (mk != 0u) cnt0 = k + 1;
-    }
-    int pid = it < nsl ? (int)__ldg(spat + slice_lo + it) : 255;
-    for (; it < nsl; it += stride) {
-        const int sl = slice_lo + it;
-        const int pid_next = (it + stride < nsl) ? (int)__ldg(spat + sl + stride) : 255;
+    auto pids_of = [&](int item) -> int {                 // both pattern numbers of an item in one 16-bit word
+        if (item >= items) return 0xffff;
+        const int sl = slice_lo + 2 * item;
+        const int a = (int)__ldg(spat + sl);
+        const int b = (sl + 1 < slice_hi) ? (int)__ldg(spat + sl + 1) : 254;      // 254: no such slice
+        return a | (b << 8);
+    };
+    int pids = pids_of(it);
+    for (; it < items; it += stride) {
+        const int pids_next = pids_of(it + stride);
+        const int sl = slice_lo + 2 * it;
         const int row = sl * 32 + lane;
         const char* xr = reinterpret_cast<const char*>(x + row);
-        double sum = 0.0;
-        if (pid == 0 && fast0) {
+        // Of the CNT gathers of a row only the one with the largest offset is new data (a stencil re-reads everything else from
+        // L1/L2), so the gathers in flight cover few DRAM bytes: pull the leading edge of x into L2 kPrefetch iterations ahead.
+        if (prefetch > 0 && it + prefetch * stride < items) {
+            const char* pf = xr + (size_t)prefetch * stride * 512 + PP.e0[CNT - 1].offb;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 256));
+        }
+        double sum[2] = {0.0, 0.0};
+        if (pids == 0) {
+            // two interior slices: every entry on every lane
+            double xa[CNT], xb[CNT];
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                if (k < cnt0) sum = fma(v0[k], *reinterpret_cast<const double*>(xr + o0[k]), sum);
-        } else if (pid != 255) {
+            for (int k = 0; k < CNT; ++k) {
+                xa[k] = *reinterpret_cast<const double*>(xr + PP.e0[k].offb);
+                xb[k] = *reinterpret_cast<const double*>(xr + 256 + PP.e0[k].offb);
+            }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const PatEnt e = PP.e[pid][k];
-                if ((e.mask >> lane) & 1u) sum = fma(e.v, *reinterpret_cast<const double*>(xr + e.offb), sum);
+            for (int k = 0; k < CNT; ++k) {
+                sum[0] = fma(PP.e0[k].v, xa[k], sum[0]);
+                sum[1] = fma(PP.e0[k].v, xb[k], sum[1]);
             }
         } else {
-            const int32_t p0 = __ldg(slice_ptr + sl), nb = __ldg(slice_ptr + sl + 1) - p0;
-            for (int b = 0; b < nb; ++b) {
-                const uint2 w = __ldg(codes + (((size_t)(p0 + b)) << 5) + lane);
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const unsigned int half = q < 4 ? w.x : w.y;
-                    const unsigned int c16 = ((q & 3) == 0 ? (half << 4) : (half >> (8 * (q & 3) - 4))) & 0xff0u;
-                    if (c16 != 0xff0u) {
-                        const DictEnt& e = *reinterpret_cast<const DictEnt*>(reinterpret_cast<const char*>(D.e) + c16);
-                        sum = fma(e.v, *reinterpret_cast<const double*>(xr + e.offb), sum);
+            for (int i = 0; i < 2; ++i) {
+                const int pid = (pids >> (8 * i)) & 0xff;
+                const char* xi = xr + 256 * i;
+                if (pid < 32) {
+#pragma unroll
+                    for (int k = 0; k < CNT; ++k)
+                        if (PP.mask[pid][k] & lanebit) sum[i] = fma(PP.e0[k].v, *reinterpret_cast<const double*>(xi + PP.e0[k].offb), sum[i]);
+                } else if (pid == 255) {
+                    const int32_t p0 = __ldg(slice_ptr + sl + i), nb = __ldg(slice_ptr + sl + i + 1) - p0;
+                    for (int b = 0; b < nb; ++b) {
+                        const uint2 w = __ldg(codes + (((size_t)(p0 + b)) << 5) + lane);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const unsigned int half = q < 4 ? w.x : w.y;
+                            const unsigned int c16 = ((q & 3) == 0 ? (half << 4) : (half >> (8 * (q & 3) - 4))) & 0xff0u;
+                            if (c16 != 0xff0u) {
+                                const DictEnt& e = *reinterpret_cast<const DictEnt*>(reinterpret_cast<const char*>(D.e) + c16);
+                                sum[i] = fma(e.v, *reinterpret_cast<const double*>(xi + e.offb), sum[i]);
+                            }
+                        }
                     }
                 }
             }
         }
-        if (row < n_loc) {
-            if (NEWTON) sum = newton_epilogue(sum, x[row], pair != 0.0 ? xprev[row] : 0.0, shift, pair);
-            y[row] = sum;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = row + 32 * i;
+            if (r < n_loc && ((pids >> (8 * i)) & 0xff) != 254) {
+                double v = sum[i];
+                if (NEWTON) v = newton_epilogue(v, x[r], pair != 0.0 ? xprev[r] : 0.0, shift, pair);
+                y[r] = v;
+            }
         }
-        pid = pid_next;
+        pids = pids_next;
     }
 }
 
-template <bool NEWTON>
+template <bool NEWTON, int CNT>
 int launch_selp_t(calz_mat* m, const double* x, const double* xp, double* y, int64_t s0, int64_t s1, double shift, double pair) {
     if (s1 <= s0) return CALZ_OK;
     calz_ctx* ctx = m->ctx;
     static int occ = 0;
     if (!occ) {
-        CALZ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_selp<NEWTON>, kSpmvThreads, 0));
+        CALZ_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_spmv_selp<NEWTON, CNT>, kSpmvThreads, 0));
         if (occ < 1) occ = 1;
     }
-    const int64_t per_cta = kSpmvThreads / 32;
+    const int64_t per_cta = 2 * (kSpmvThreads / 32);
     const unsigned grid = (unsigned)std::min<int64_t>((s1 - s0 + per_cta - 1) / per_cta, (int64_t)ctx->num_sms * occ);
     static_assert(sizeof(PatParam) == sizeof(m->h_pat), "pattern parameter block");
-    k_spmv_selp<NEWTON><<<grid, kSpmvThreads, 0, ctx->stream>>>(m->d_slice_pat, m->d_slice_ptr, (const uint2*)m->d_codes,
-                                                                 *(const DictParam*)m->h_dict, *(const PatParam*)m->h_pat, x, xp, y, (int)s0,
-                                                                 (int)s1, (int)m->n_loc, shift, pair);
+    k_spmv_selp<NEWTON, CNT><<<grid, kSpmvThreads, 0, ctx->stream>>>(m->d_slice_pat, m->d_slice_ptr, (const uint2*)m->d_codes,
+                                                                      *(const DictParam*)m->h_dict, *(const PatParam*)m->h_pat, x, xp, y,
+                                                                      (int)s0, (int)s1, (int)m->n_loc, shift, pair, (int)ctx->opt_mpk_prefetch);
     CALZ_LAUNCH_CHECK(ctx);
     return CALZ_OK;
+}
+
+template <bool NEWTON>
+int launch_selp(calz_mat* m, const double* x, const double* xp, double* y, int64_t s0, int64_t s1, double shift, double pair) {
+    switch (m->pat_cnt0) {
+        case 1: return launch_selp_t<NEWTON, 1>(m, x, xp, y, s0, s1, shift, pair);
+        case 2: return launch_selp_t<NEWTON, 2>(m, x, xp, y, s0, s1, shift, pair);
+        case 3: return launch_selp_t<NEWTON, 3>(m, x, xp, y, s0, s1, shift, pair);
+        case 4: return launch_selp_t<NEWTON, 4>(m, x, xp, y, s0, s1, shift, pair);
+        case 5: return launch_selp_t<NEWTON, 5>(m, x, xp, y, s0, s1, shift, pair);
+        case 6: return launch_selp_t<NEWTON, 6>(m, x, xp, y, s0, s1, shift, pair);
+        case 7: return launch_selp_t<NEWTON, 7>(m, x, xp, y, s0, s1, shift, pair);
+        default: return launch_selp_t<NEWTON, 8>(m, x, xp, y, s0, s1, shift, pair);
+    }
 }
 
 // ---- the matrix powers kernel proper: ALL steps of one exchange group in ONE cooperative launch.  Step k sweeps the slices
@@ -563,8 +603,8 @@ int launch_selld(calz_mat* m, const double* x, const double* xp, double* y, int6
     if (dm < 0) dm = m->dict_uniform >= 0.75 ? DM_CONST : DM_SHARED;
     const int key = (newton ? 1 : 0) | (ctx->opt_mpk_persist ? 2 : 0) | (dm << 2);
     if (!newton) { shift = 0.0; pair = 0.0; }
-    if (ctx->opt_mpk_patterns && dm == DM_CONST && m->d_slice_pat && m->pat_cover >= 0.5)      // most slices have a pattern: no codes at all
-        return newton ? launch_selp_t<true>(m, x, xp, y, s0, s1, shift, pair) : launch_selp_t<false>(m, x, xp, y, s0, s1, shift, pair);
+    if (ctx->opt_mpk_patterns && dm == DM_CONST && m->d_slice_pat && m->pat_cover >= 0.5 && m->pat_cnt0 >= 1)   // most slices have a pattern
+        return newton ? launch_selp<true>(m, x, xp, y, s0, s1, shift, pair) : launch_selp<false>(m, x, xp, y, s0, s1, shift, pair);
 #define CALZ_SELLD_CASE(NW, PS, DM) \
     case ((NW) | ((PS) << 1) | ((DM) << 2)): return launch_selld_t<NW != 0, PS != 0, DM>(m, x, xp, y, s0, s1, shift, pair);
     switch (key) {

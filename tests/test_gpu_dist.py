@@ -37,3 +37,16 @@ def test_two_rank_scattered_exchange_powerlaw(backend):
            "--backend", backend]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+@pytest.mark.parametrize("extra", [["--halo-level", "4"], ["--halo-level", "1"], ["--own-rows-only"]])
+def test_two_rank_multi_exchange_matrix_powers(extra):
+    # ghost closure shallower than s: the MPK exchanges the current basis column every L steps (L = 4: two exchanges per block;
+    # L = 1: the classic per-step exchange, what a rank that only holds its own rows of A gets)
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29553", os.path.join(ROOT, "tests", "dist_check.py"), "--grid", "32", "--backend", "cholqr2"] + extra
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+

@@ -68,18 +68,6 @@ def test_long_rows_take_the_segmented_kernel(layout):
     dm.close()
 
 
-def test_powerlaw_rows_generator_matches_whole_matrix():
-    """the per-rank generator of the C4 matrix: any row slice equals the same rows of the whole matrix, symmetric, SPD by dominance"""
-    n = 4000
-    A = gallery.powerlaw_spd_rows(n, 10.0, seed=3)
-    assert abs(A - A.T).max() == 0
-    d = A.diagonal()
-    assert np.all(d - (abs(A).sum(axis=1).A1 - d) >= 1.0 - 1e-12)
-    for lo, hi in ((0, 500), (1234, 3000), (3000, 4000)):
-        S = gallery.powerlaw_spd_rows(n, 10.0, seed=3, row_lo=lo, row_hi=hi)
-        assert abs(S - A[lo:hi]).max() == 0
-
-
 @pytest.mark.parametrize("layout", ["csr", "sell"])
 @pytest.mark.parametrize("name", list(MATS))
 def test_spmv_and_monomial(name, layout):

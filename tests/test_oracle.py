@@ -219,3 +219,82 @@ def test_leja_shifts_agree_with_the_surveys_independent_restatement_up_to_the_ti
     same = np.allclose(mine[2:], survey[2:], atol=5e-5)
     mirrored = np.allclose(mine[2:], 101.0 - survey[2:], atol=5e-5)
     assert same or mirrored
+
+
+# ---------------------------------------------------------------------------------------------- round 2 additions
+def test_powerlaw_rows_generator_matches_whole_matrix():
+    """the per-rank generator of the C4 matrix: any row slice equals the same rows of the whole matrix, symmetric, SPD by dominance"""
+    n = 4000
+    A = gallery.powerlaw_spd_rows(n, 10.0, seed=3)
+    assert abs(A - A.T).max() == 0
+    d = A.diagonal()
+    assert np.all(d - (abs(A).sum(axis=1).A1 - d) >= 1.0 - 1e-12)
+    for lo, hi in ((0, 500), (1234, 3000), (3000, 4000)):
+        S = gallery.powerlaw_spd_rows(n, 10.0, seed=3, row_lo=lo, row_hi=hi)
+        assert abs(S - A[lo:hi]).max() == 0
+
+
+
+def test_powerlaw_rows_generator_jacobi_scaling():
+    n = 3000
+    A = gallery.powerlaw_spd_rows(n, 10.0, seed=3, jacobi=True)
+    A0 = gallery.powerlaw_spd_rows(n, 10.0, seed=3)
+    d = 1.0 / np.sqrt(A0.diagonal())
+    import scipy.sparse as sp
+    assert abs(sp.diags(d) @ A0 @ sp.diags(d) - A).max() < 1e-15
+    assert abs(A - A.T).max() == 0 and np.all(A.diagonal() == 1.0)
+    S = gallery.powerlaw_spd_rows(n, 10.0, seed=3, row_lo=777, row_hi=1999, jacobi=True)
+    assert abs(S - A[777:1999]).max() == 0
+    ev = np.linalg.eigvalsh(A.toarray())
+    assert ev[0] > 0 and ev[-1] < 2.0                               # SPD, spectrum of a normalised Laplacian + I scaled
+
+
+def test_periodic_driver_on_the_references_own_diagonal_test():
+    """test_convergence_diagonal_matrices.m:9-22: diag(linspace(1,100,500)), r = ones, 480 steps, s = 8 Newton, PERIODIC
+    orthogonalisation (ca_lanczos.m:362-467 with update_omega :469-539 / reset_omega :541-551).  The eigenvalues are known
+    analytically (the diagonal): the restated driver must converge to them and keep semi-orthogonality."""
+    from oracle import drivers
+    N = 500
+    A = gallery.diag_linspace(N, 100.0)
+    io = {}
+    T, Q = drivers.ca_lanczos(A, np.ones(N), 8, 480, "newton", "periodic", info=io)
+    ev = np.sort(np.linalg.eig(T)[0].real)[::-1]
+    exact = np.linspace(1.0, 100.0, N)[::-1]
+    np.testing.assert_allclose(ev[:20], exact[:20], rtol=1e-10)
+    assert io["nbreaks"] >= 10 and io["breaks"] == sorted(io["breaks"])
+    assert np.linalg.norm(np.eye(Q.shape[1]) - Q.T @ Q) < 1e-7      # sqrt(eps)-level semi-orthogonality, by construction
+    # 'local' on the same problem loses orthogonality completely: the test would fail without the omega recurrence
+    Tl, Ql = drivers.ca_lanczos(A, np.ones(N), 8, 480, "newton", "local")
+    assert np.linalg.norm(np.eye(Ql.shape[1]) - Ql.T @ Ql) > 1.0
+
+
+def test_omega_recurrence_product_restatement_equals_oracle():
+    """solver.update_omega / reset_omega (product, host algebra of the device driver) against oracle.drivers (test infrastructure)"""
+    from ca_lanczos_b200 import solver
+    from oracle import drivers
+    rng = np.random.default_rng(0)
+    s = 4
+    om_o = om_s = None
+    for k in range(1, 6):
+        alpha = rng.uniform(1, 2, s * k); beta = rng.uniform(0.1, 1, s * k)
+        om_o = drivers.update_omega(om_o, alpha, beta, 3.0, s)
+        om_s = solver.update_omega(om_s, alpha, beta, 3.0, s)
+        np.testing.assert_array_equal(om_o, om_s)
+        if k == 3:
+            om_o = drivers.reset_omega(om_o, 3.0, s); om_s = solver.reset_omega(om_s, 3.0, s)
+            np.testing.assert_array_equal(om_o, om_s)
+
+
+def test_halo_level_rule_and_multi_exchange_mpk():
+    from oracle import partition
+    A = gallery.laplace3d(8, 8, 64)
+    assert partition.choose_halo_level(A, 8, 8) == 4                # 8 planes per rank: 2 x 4 ghost planes <= 8 owned
+    assert partition.choose_halo_level(A, 2, 8) == 8
+    B = gallery.powerlaw_spd(3000, 6.0, seed=1)
+    assert partition.choose_halo_level(B, 4, 4) == 1                # the level-1 closure is (almost) every row
+    v = np.cos(np.arange(B.shape[0]) * 0.37) + 2.0
+    lam = np.array([30.0, 2.0, 15.0, 7.0])
+    one = partition.mpk_partitioned(B, v, 4, lam, 1)
+    for P, L in ((4, 1), (3, 2), (2, 4)):
+        many = partition.mpk_partitioned(B, v, 4, lam, P, halo_level=L)
+        assert np.max(np.abs(many - one)) <= 1e-13 * np.max(np.abs(one))
