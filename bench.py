@@ -59,7 +59,8 @@ def parse():
     ap.add_argument("--config", default="c3", choices=["c3", "c4", "c5"],
                     help="c3 (default): the BASELINE workload the metric is quoted on; c4: restarted_ca_lanczos on the power-law SPD matrix "
                          "(s=6, TSQR); c5: TSQR vs CholQR sweep on n x (s+1) blocks -- c4/c5 are extra lines kept under profiles/")
-    ap.add_argument("--n", type=int, default=0, help="c4: matrix order (default 2e7); c5: total rows (default 1e8)")
+    ap.add_argument("--size", dest="n", type=int, default=0,
+                    help="c4: matrix order (default 2e7); c5: total rows (default 1e8)  [not --n: torchrun prefix-matches its own options]")
     ap.add_argument("--orth", default="full", choices=["local", "full"],
                     help="c4: orthogonalisation of restarted_ca_lanczos ('local' is the reference default; on this matrix it loses "
                          "orthogonality within the first cycle in the reference as well -- see DESIGN.md)")
@@ -466,7 +467,11 @@ def run_b200(args):
     #  copy peak; the compression gain is reported separately as `algorithmic_speedup`.
     own_nnz = nnz if world == 1 else int(round(nnz * n_own / n))
     alg_bytes = 12 * own_nnz + 4 * (n_own + 1) + 16 * n_own
-    if dm.layout == "selld":
+    patterns = dm.layout == "selld" and dm.info("pattern_cover_pct") >= 50 and os.environ.get("CALZ_OPTS", "").find("mpk_patterns=0") < 0
+    if patterns:      # slice-pattern kernel: one pattern byte per slice, code bytes only for the slices without a pattern, x and y
+        cover = dm.info("pattern_cover_pct") / 100.0
+        moved = int((1.0 - cover) * dm.info("sell_padded_nnz")) + n_loc // 32 + 16 * n_loc
+    elif dm.layout == "selld":
         moved = dm.info("sell_padded_nnz") + 4 * (n_loc // 32 + 2) + 16 * n_loc
     elif dm.layout == "sell":
         moved = 12 * dm.info("sell_padded_nnz") + 4 * (n_loc // 32 + 1) + 16 * n_loc
@@ -475,7 +480,7 @@ def run_b200(args):
     launch_ms = ms_mpk / s
     achieved = moved / (launch_ms * 1e-3) / 1e9
     traffic = None
-    kname = {"selld": "k_spmv_selld", "sell": "k_spmv_sell", "csr": "k_spmv_csr"}.get(dm.layout, "k_spmv")
+    kname = "k_spmv_selp" if patterns else {"selld": "k_spmv_selld", "sell": "k_spmv_sell", "csr": "k_spmv_csr"}.get(dm.layout, "k_spmv")
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             tj = json.load(f)
@@ -643,9 +648,9 @@ def run_c4(args):
     backend = "tsqr" if args.backend == "cholqr2" else args.backend
     orth = args.orth
 
-    # ---- untimed checker: the same N-rank code path at n = 6000, converged eigenvalues against the dense LAPACK spectrum
+    # ---- untimed checker: the same N-rank code path at n = 3000, converged eigenvalues against the dense LAPACK spectrum
     def small_check():
-        ns = 6000
+        ns = 3000
         l0, h0 = (rank * ns) // world, ((rank + 1) * ns) // world
         As = gallery.powerlaw_spd_rows(ns, 20.0, seed=0, row_lo=l0, row_hi=h0, jacobi=True)
         dms = api.DeviceMatrix(As, s_max=s, layout=args.layout, ctx=ctx, n_glob=ns, row_begin=l0)
@@ -660,11 +665,15 @@ def run_c4(args):
         dms.close()
         return out
     check = None if args.no_parity else small_check()
+    if world > 1:
+        dist.barrier()                    # rank 0 spent ~30 s in LAPACK: re-align the ranks before the next device collective
 
     lo, hi = (rank * n) // world, ((rank + 1) * n) // world
     t0 = time.time()
     A = gallery.powerlaw_spd_rows(n, 20.0, seed=0, row_lo=lo, row_hi=hi, jacobi=True)
     gen_s = time.time() - t0
+    if world > 1:
+        dist.barrier()                    # generation time differs from rank to rank
     nnz_own = int(A.nnz)
     colsum = np.asarray(abs(A).sum(axis=1)).ravel()          # symmetric: column sums of |A| restricted to the owned columns
     maxrow = int(np.diff(A.indptr).max())

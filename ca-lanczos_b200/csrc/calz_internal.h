@@ -75,6 +75,7 @@ struct calz_ctx {
     calz::NcclApi* nccl = nullptr;
     calz::ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
+    int setup_depth = 0;             // > 0 while a set-up phase runs: small all-reduces use NCCL, not the peer-memory mailbox
 
     // options
     int64_t opt_l2_chunk_bytes = 0;

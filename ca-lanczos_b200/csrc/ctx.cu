@@ -90,7 +90,9 @@ int nccl_load(const char* path, NcclApi** api, std::string* err) {
 
 int allreduce_sum(calz_ctx* ctx, double* dev, size_t count) {
     if (ctx->nranks <= 1 || count == 0) return CALZ_OK;
-    if (p2p_allreduce_ok(ctx, count)) return p2p_allreduce(ctx, dev, count);
+    // set-up phases (matrix creation) go through NCCL: ranks may arrive tens of seconds apart there (host-side matrix generation),
+    // which a stream-ordered NCCL collective simply waits out while the bounded spins of the peer-memory kernels would time out
+    if (ctx->setup_depth == 0 && p2p_allreduce_ok(ctx, count)) return p2p_allreduce(ctx, dev, count);
     CALZ_NCCL(ctx, ctx->nccl->AllReduce(dev, dev, count, ncclFloat64, ncclSum, ctx->comm, ctx->stream));
     return CALZ_OK;
 }

@@ -120,6 +120,7 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
         return set_error(ctx, CALZ_ERR_BADARG, "calz_mat_create_csr: bad arguments");
     *out = nullptr;
     CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    struct SetupGuard { calz_ctx* c; explicit SetupGuard(calz_ctx* c_) : c(c_) { c->setup_depth++; } ~SetupGuard() { c->setup_depth--; } } setup_guard(ctx);
     const int P = ctx->nranks, me = ctx->rank;
     std::vector<int64_t> bounds(P + 1);
     calz_partition_bounds(n_glob, P, bounds.data());

@@ -4,7 +4,7 @@
 
 namespace calz {
 
-constexpr unsigned long long kSpinLimit = 20ull * 1000ull * 1000ull;      // ~10-20 s; a healthy wait is microseconds
+constexpr unsigned long long kSpinLimit = 100ull * 1000ull * 1000ull;     // ~1 min; a healthy wait is microseconds
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
     unsigned long long v;

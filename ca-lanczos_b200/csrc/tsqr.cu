@@ -27,6 +27,10 @@ namespace {
 
 constexpr int kTsqrThreads = 128;                // 4 warps per leaf; RPL rows per thread (RPL*CW <= 64 doubles of the leaf per thread)
 constexpr int kTsqrWarps = kTsqrThreads / 32;
+#ifndef CALZ_TSQR_LEAF_CTAS8
+#define CALZ_TSQR_LEAF_CTAS8 3
+#endif
+constexpr int kLeafCtas8 = CALZ_TSQR_LEAF_CTAS8;      // resident leaf CTAs per SM for c <= 8 (3: <= 168 registers per thread)
 
 // compile-time loop: f(std::integral_constant<int, I>) for I = B .. E-1
 template <int B, int E, class F>
@@ -86,7 +90,7 @@ __device__ __forceinline__ double cta_reduce_get(const double* red, int KP, int 
 // keeps v_i'v_j (the compact-WY data the top-down sweep needs, see k_tsqr_apply); barrier; every thread scales its part of the
 // reflector and updates its rows.
 template <int CW, int RPL>
-__global__ void __launch_bounds__(kTsqrThreads, 2)
+__global__ void __launch_bounds__(kTsqrThreads, (CW <= 8 ? kLeafCtas8 : 2))
 k_tsqr_leaf(long long nrows, int c, const double* A, long long ldA, double* V, long long ldV, double* __restrict__ tau_out,
             double* __restrict__ Rstack, long long ldR, double* __restrict__ Gout, const int* __restrict__ pred, int want) {
     if (pred && *pred != want) return;
