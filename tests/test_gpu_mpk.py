@@ -175,10 +175,27 @@ def test_slice_patterns_of_a_stencil():
     """7-point Laplacian 64 x 40 x 33: 2 slices per grid line, the line ends miss one neighbour on one lane (lane masks); the three
     boundary states of y and z give 27 patterns at most and every complete slice has one; pattern 0 is the interior."""
     A = gallery.laplace3d(64, 40, 33)
+    n = A.shape[0]
+    ctx = api.default_context()
+    ref_dm = api.DeviceMatrix(A, 4, "sell")
+    v = np.cos(0.11 * np.arange(n)) + 0.3
+    lam = np.array([5.0, 0.5, 3.0, 1.0])
+    ref = (api.matrix_powers_newton(ref_dm, v, 4, lam, 1), api.matrix_powers_monomial(ref_dm, v, 3))
+    ref_dm.close()
     dm = api.DeviceMatrix(A, 4, "selld")
     assert 1 <= dm.info("n_patterns") <= 32
     assert dm.info("pattern_cover_pct") >= 99
-    dm.close()
+    assert dm.info("ring_rows") in (256, 512, 1024)
+    try:
+        for ring, prefetch in ((1, 1), (0, 1), (0, 0), (0, 8)):    # TMA-ring kernel / gather kernel with several prefetch distances
+            ctx.set_option("mpk_ring", ring)
+            ctx.set_option("mpk_prefetch", prefetch)
+            np.testing.assert_array_equal(api.matrix_powers_newton(dm, v, 4, lam, 1), ref[0])
+            np.testing.assert_array_equal(api.matrix_powers_monomial(dm, v, 3), ref[1])
+    finally:
+        ctx.set_option("mpk_ring", 1)
+        ctx.set_option("mpk_prefetch", 1)
+        dm.close()
 
 
 @pytest.mark.parametrize("name", ["poisson100", "lap3d"])
