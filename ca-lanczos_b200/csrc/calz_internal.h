@@ -90,7 +90,6 @@ struct calz_ctx {
     int64_t opt_mpk_halo_level = 0;  // depth of the ghost closure = MPK steps per halo exchange (0: automatic, see matrix.cu)
     int64_t opt_mpk_prefetch = 1;    // slice-pattern kernel: L2 prefetch distance of the leading edge of x, in warp iterations
                                      // (measured per C3 MPK: 0 -> 0.911 ms, 1 -> 0.765, 2 -> 0.773, 4 -> 0.779, 8 -> 0.790, 16 -> 0.911)
-    int64_t opt_mpk_ring = 1;        // slice-pattern kernel with the x segments staged by TMA in a shared-memory ring (k_spmv_selr)
     int64_t opt_mpk_patterns = 1;    // dictionary SELL: slice-pattern kernel (k_spmv_selp) when most slices have a pattern
     int64_t opt_mpk_fused_steps = 0; // dictionary SELL: all steps of an exchange group in one cooperative launch (grid barriers); measured: no gain over
                                      // back-to-back launches (0.848 vs 0.850 ms per C3 MPK, 0.182 vs 0.176 ms on a 2.6 M-row slab) => off

@@ -249,7 +249,6 @@ int calz_set_option(calz_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "mpk_fused_steps")) ctx->opt_mpk_fused_steps = value;
     else if (!strcmp(key, "mpk_patterns")) ctx->opt_mpk_patterns = value;
     else if (!strcmp(key, "mpk_prefetch")) ctx->opt_mpk_prefetch = value;
-    else if (!strcmp(key, "mpk_ring")) ctx->opt_mpk_ring = value;
     else if (!strcmp(key, "mpk_dict_mode")) ctx->opt_mpk_dict_mode = value;
     else if (!strcmp(key, "mpk_xs_rows")) ctx->opt_mpk_xs_rows = value;
     else if (!strcmp(key, "tile_pipeline")) ctx->opt_tile_pipeline = value;

@@ -597,34 +597,6 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
                     if (prov[sl] >= 0 && newid[prov[sl]] >= 0) { spat[sl] = (uint8_t)newid[prov[sl]]; ++covered; }
             }
             m->pat_cover = m->sell_slices ? (double)covered / (double)m->sell_slices : 0.0;
-            // ---- staging plan of the TMA-ring kernel: group the offsets of pattern 0 (ascending in e0) into segments
-            if (m->pat_cnt0 >= 1) {
-                for (int R : {1024, 512, 256}) {
-                    int ng = 0, total = 0, omin[8], omax[8], grp[8];
-                    bool ok = true;
-                    for (int k = 0; k < m->pat_cnt0 && ok; ++k) {
-                        const int o = m->h_pat->e0[k].offb / 8;
-                        if (ng > 0 && (int64_t)o - omax[ng - 1] < R) omax[ng - 1] = o;
-                        else if (ng < 8) { omin[ng] = o; omax[ng] = o; ++ng; }
-                        else ok = false;
-                        grp[k] = ng - 1;
-                    }
-                    if (!ok) continue;
-                    int base[8], len[8], amin[8];
-                    for (int g = 0; g < ng; ++g) {
-                        amin[g] = omin[g] - (((omin[g] % 2) + 2) % 2);           // even, <= omin
-                        len[g] = R + (omax[g] - amin[g]) + 2;
-                        len[g] += len[g] & 1;
-                        base[g] = total;
-                        total += len[g];
-                    }
-                    if ((size_t)total * 8 * 3 > 108 * 1024 || n_loc < 4 * R) continue;
-                    m->xr_rows = R; m->xr_groups = ng; m->xr_total = total;
-                    for (int g = 0; g < ng; ++g) { m->xr_amin[g] = amin[g]; m->xr_len[g] = len[g]; m->xr_base[g] = base[g]; }
-                    for (int k = 0; k < m->pat_cnt0; ++k) m->xr_soff[k] = base[grp[k]] + (m->h_pat->e0[k].offb / 8 - amin[grp[k]]);
-                    break;
-                }
-            }
             CALZ_TRY(upload(ctx, &m->d_slice_pat, spat));
         }
         m->sell_padded = blocks * 256;
@@ -782,7 +754,6 @@ int calz_mat_info(const calz_mat* m, const char* what, int64_t* value) {
     else if (!strcmp(what, "dict_size")) *value = m->dict_size;
     else if (!strcmp(what, "dict_uniform_pct")) *value = (int64_t)(100.0 * m->dict_uniform);
     else if (!strcmp(what, "n_patterns")) *value = m->n_pat;
-    else if (!strcmp(what, "ring_rows")) *value = m->xr_rows;
     else if (!strcmp(what, "pattern_cover_pct")) *value = (int64_t)(100.0 * m->pat_cover);
     else if (!strcmp(what, "xs_rows")) *value = m->xs_rows;
     else if (!strcmp(what, "xs_groups")) *value = m->xs_groups;

@@ -76,10 +76,6 @@ struct calz_mat {
     int pat_cnt0 = 0;                                 // entries of pattern 0; 0: no usable pattern 0 (it must cover all 32 lanes)
     double pat_cover = 0.0;                           // fraction of the slices that have a pattern
     uint8_t* d_slice_pat = nullptr;                   // per slice: pattern number, 255 = none (coded path)
-    // x staging plan of the TMA-ring pattern kernel (k_spmv_selr): a tile of xr_rows rows needs, per group of nearby offsets, one
-    // contiguous segment of x; xr_soff[k] = position of x[row0 + offset_k] inside a stage (entry k of pattern 0)
-    int xr_rows = 0, xr_groups = 0, xr_total = 0;
-    int xr_amin[8] = {}, xr_len[8] = {}, xr_base[8] = {}, xr_soff[8] = {};
     // ... and its TMA-staged kernel: x segments of a CTA's row block (merged over overlapping offsets)
     int xs_rows = 0;                                  // rows per CTA (0: staged kernel not applicable)
     int xs_groups = 0;

@@ -333,175 +333,6 @@ int launch_selp_t(calz_mat* m, const double* x, const double* xp, double* y, int
     return CALZ_OK;
 }
 
-// ---- slice patterns with the x vector staged by TMA (north_star: "x-vector and ghost-zone staging in shared memory/TMA").
-//      A persistent CTA streams tiles of RP.rows consecutive rows; for each tile a producer warp issues one bulk copy
-//      (cp.async.bulk, mbarrier complete_tx) per SEGMENT of x -- the offsets of the stencil fall into a few groups of nearby
-//      offsets (7-point 256^3: {-65536}, {-256..+256}, {+65536}), each needs rows+span contiguous doubles -- into a ring of
-//      shared-memory stages; 8 consumer warps then read their gathers from shared memory (no L1/L2 latency on the critical path)
-//      and store y.  Every x element crosses HBM once, the re-reads of the stencil come from L2 in bulk.  Same products, same
-//      order as every other SpMV kernel here: bit-identical.
-constexpr int kRingConsumers = 8;
-constexpr int kRingThreads = (kRingConsumers + 1) * 32;
-struct RingPlan {
-    int rows, groups, total;
-    int amin[8], len[8], base[8];
-    int soff[8];                              // entry k of pattern 0 reads xs[soff[k] + local row]
-    int center;                               // soff of the offset-0 entry, -1 if there is none (x[row] for the Newton epilogue)
-};
-
-__device__ __forceinline__ uint32_t ring_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ring_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(ring_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-
-template <bool NEWTON, int CNT>
-__global__ void __launch_bounds__(kRingThreads, 2)
-k_spmv_selr(const uint8_t* __restrict__ spat, const int32_t* __restrict__ slice_ptr, const uint2* __restrict__ codes,
-            const __grid_constant__ DictParam D, const __grid_constant__ PatParam PP, const __grid_constant__ RingPlan RP,
-            const double* __restrict__ x, const double* __restrict__ xprev, double* __restrict__ y, int tile_lo, int tile_hi,
-            int row_lo, int row_hi, int n_loc, long long ldw, double shift, double pair, int stages) {
-    extern __shared__ __align__(128) unsigned char ring_raw[];
-    double* ring = reinterpret_cast<double*>(ring_raw);
-    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)stages * RP.total);
-    uint64_t* empty = full + stages;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) {
-        for (int s = 0; s < stages; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ring_u32(&full[s])), "r"(1) : "memory");
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ring_u32(&empty[s])), "r"(kRingConsumers) : "memory");
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    const int R = RP.rows;
-    if (warp == kRingConsumers) {
-        // ================================================= producer: one elected lane issues the bulk copies of a tile
-        if (lane == 0) {
-            int it = 0;
-            for (int t = tile_lo + (int)blockIdx.x; t < tile_hi; t += (int)gridDim.x, ++it) {
-                const int s = it % stages;
-                ring_wait(&empty[s], (uint32_t)(((it / stages) & 1) ^ 1));
-                double* dst = ring + (size_t)s * RP.total;
-                const long long r0 = (long long)t * R;
-                long long lo[8], hi[8];
-                uint32_t bytes = 0;
-                for (int g = 0; g < RP.groups; ++g) {
-                    lo[g] = max(r0 + RP.amin[g], 0LL);
-                    hi[g] = min(r0 + RP.amin[g] + RP.len[g], ldw);
-                    if (hi[g] > lo[g]) bytes += (uint32_t)((hi[g] - lo[g]) * 8);
-                }
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ring_u32(&full[s])), "r"(bytes) : "memory");
-                for (int g = 0; g < RP.groups; ++g) {
-                    if (hi[g] <= lo[g]) continue;
-                    double* d = dst + RP.base[g] + (lo[g] - (r0 + RP.amin[g]));
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(ring_u32(d)), "l"(x + lo[g]), "r"((uint32_t)((hi[g] - lo[g]) * 8)), "r"(ring_u32(&full[s])) : "memory");
-                }
-            }
-        }
-        return;
-    }
-    // ===================================================== consumers
-    const unsigned lanebit = 1u << lane;
-    const int spt = R / 32;                               // slices per tile
-    int it = 0;
-    for (int t = tile_lo + (int)blockIdx.x; t < tile_hi; t += (int)gridDim.x, ++it) {
-        const int s = it % stages;
-        // pattern numbers of this warp's slices, one per lane, fetched before waiting for the tile
-        const int sl0 = t * spt;
-        const int my_pid = (lane < spt) ? (int)__ldg(spat + sl0 + lane) : 255;
-        ring_wait(&full[s], (uint32_t)((it / stages) & 1));
-        const double* xs = ring + (size_t)s * RP.total;
-        for (int j = warp; j < spt; j += kRingConsumers) {
-            const int pid = __shfl_sync(0xffffffffu, my_pid, j);
-            const int i = j * 32 + lane;                  // local row
-            const int row = t * R + i;
-            double sum = 0.0;
-            if (pid == 0) {
-#pragma unroll
-                for (int k = 0; k < CNT; ++k) sum = fma(PP.e0[k].v, xs[RP.soff[k] + i], sum);
-            } else if (pid < 32) {
-#pragma unroll
-                for (int k = 0; k < CNT; ++k)
-                    if (PP.mask[pid][k] & lanebit) sum = fma(PP.e0[k].v, xs[RP.soff[k] + i], sum);
-            } else {
-                const char* xi = reinterpret_cast<const char*>(x + row);
-                const int sl = sl0 + j;
-                const int32_t p0 = __ldg(slice_ptr + sl), nb = __ldg(slice_ptr + sl + 1) - p0;
-                for (int b = 0; b < nb; ++b) {
-                    const uint2 w = __ldg(codes + (((size_t)(p0 + b)) << 5) + lane);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const unsigned int half = q < 4 ? w.x : w.y;
-                        const unsigned int c16 = ((q & 3) == 0 ? (half << 4) : (half >> (8 * (q & 3) - 4))) & 0xff0u;
-                        if (c16 != 0xff0u) {
-                            const DictEnt& e = *reinterpret_cast<const DictEnt*>(reinterpret_cast<const char*>(D.e) + c16);
-                            sum = fma(e.v, *reinterpret_cast<const double*>(xi + e.offb), sum);
-                        }
-                    }
-                }
-            }
-            if (row >= row_lo && row < row_hi && row < n_loc) {
-                if (NEWTON) {
-                    const double xr = RP.center >= 0 ? xs[RP.center + i] : x[row];
-                    sum = newton_epilogue(sum, xr, pair != 0.0 ? xprev[row] : 0.0, shift, pair);
-                }
-                y[row] = sum;
-            }
-        }
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(ring_u32(&empty[s])) : "memory");
-    }
-}
-
-template <bool NEWTON, int CNT>
-int launch_selr_t(calz_mat* m, const double* x, const double* xp, double* y, int64_t lo, int64_t hi, double shift, double pair) {
-    calz_ctx* ctx = m->ctx;
-    RingPlan rp{};
-    rp.rows = m->xr_rows; rp.groups = m->xr_groups; rp.total = m->xr_total;
-    rp.center = -1;
-    for (int g = 0; g < m->xr_groups; ++g) { rp.amin[g] = m->xr_amin[g]; rp.len[g] = m->xr_len[g]; rp.base[g] = m->xr_base[g]; }
-    for (int k = 0; k < CNT; ++k) {
-        rp.soff[k] = m->xr_soff[k];
-        if (m->h_pat->e0[k].offb == 0) rp.center = m->xr_soff[k];
-    }
-    const int stages = 3;
-    const size_t smem = (size_t)stages * rp.total * sizeof(double) + 2 * 8 * sizeof(uint64_t) + 64;
-    auto kern = k_spmv_selr<NEWTON, CNT>;
-    static size_t configured = 0;
-    if (configured < smem) {
-        CALZ_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
-    int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kRingThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-    const int t0 = (int)(lo / rp.rows), t1 = (int)((hi + rp.rows - 1) / rp.rows);
-    const int grid = std::max(1, std::min(t1 - t0, ctx->num_sms * per_sm));
-    kern<<<grid, kRingThreads, smem, ctx->stream>>>(m->d_slice_pat, m->d_slice_ptr, (const uint2*)m->d_codes, *(const DictParam*)m->h_dict,
-                                                    *(const PatParam*)m->h_pat, rp, x, xp, y, t0, t1, (int)lo, (int)hi, (int)m->n_loc,
-                                                    (long long)m->ldW, shift, pair, stages);
-    CALZ_LAUNCH_CHECK(ctx);
-    return CALZ_OK;
-}
-
-template <bool NEWTON>
-int launch_selr(calz_mat* m, const double* x, const double* xp, double* y, int64_t lo, int64_t hi, double shift, double pair) {
-    switch (m->pat_cnt0) {
-        case 1: return launch_selr_t<NEWTON, 1>(m, x, xp, y, lo, hi, shift, pair);
-        case 2: return launch_selr_t<NEWTON, 2>(m, x, xp, y, lo, hi, shift, pair);
-        case 3: return launch_selr_t<NEWTON, 3>(m, x, xp, y, lo, hi, shift, pair);
-        case 4: return launch_selr_t<NEWTON, 4>(m, x, xp, y, lo, hi, shift, pair);
-        case 5: return launch_selr_t<NEWTON, 5>(m, x, xp, y, lo, hi, shift, pair);
-        case 6: return launch_selr_t<NEWTON, 6>(m, x, xp, y, lo, hi, shift, pair);
-        case 7: return launch_selr_t<NEWTON, 7>(m, x, xp, y, lo, hi, shift, pair);
-        default: return launch_selr_t<NEWTON, 8>(m, x, xp, y, lo, hi, shift, pair);
-    }
-}
-
 template <bool NEWTON>
 int launch_selp(calz_mat* m, const double* x, const double* xp, double* y, int64_t s0, int64_t s1, double shift, double pair) {
     switch (m->pat_cnt0) {
@@ -773,9 +604,6 @@ int launch_selld(calz_mat* m, const double* x, const double* xp, double* y, int6
     const int key = (newton ? 1 : 0) | (ctx->opt_mpk_persist ? 2 : 0) | (dm << 2);
     if (!newton) { shift = 0.0; pair = 0.0; }
     if (ctx->opt_mpk_patterns && dm == DM_CONST && m->d_slice_pat && m->pat_cover >= 0.5 && m->pat_cnt0 >= 1) {   // most slices have a pattern
-        // TMA ring: x and the workspace columns must be 16-byte aligned (W_pad == 0) and the pattern's offsets must fit the stage budget
-        if (ctx->opt_mpk_ring && m->xr_rows > 0 && m->W_pad == 0 && ((uintptr_t)x % 16) == 0)
-            return newton ? launch_selr<true>(m, x, xp, y, lo, hi, shift, pair) : launch_selr<false>(m, x, xp, y, lo, hi, shift, pair);
         return newton ? launch_selp<true>(m, x, xp, y, s0, s1, shift, pair) : launch_selp<false>(m, x, xp, y, s0, s1, shift, pair);
     }
 #define CALZ_SELLD_CASE(NW, PS, DM) \

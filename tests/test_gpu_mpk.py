@@ -185,15 +185,12 @@ def test_slice_patterns_of_a_stencil():
     dm = api.DeviceMatrix(A, 4, "selld")
     assert 1 <= dm.info("n_patterns") <= 32
     assert dm.info("pattern_cover_pct") >= 99
-    assert dm.info("ring_rows") in (256, 512, 1024)
     try:
-        for ring, prefetch in ((1, 1), (0, 1), (0, 0), (0, 8)):    # TMA-ring kernel / gather kernel with several prefetch distances
-            ctx.set_option("mpk_ring", ring)
+        for prefetch in (1, 0, 8):                                 # several L2 prefetch distances
             ctx.set_option("mpk_prefetch", prefetch)
             np.testing.assert_array_equal(api.matrix_powers_newton(dm, v, 4, lam, 1), ref[0])
             np.testing.assert_array_equal(api.matrix_powers_monomial(dm, v, 3), ref[1])
     finally:
-        ctx.set_option("mpk_ring", 1)
         ctx.set_option("mpk_prefetch", 1)
         dm.close()
 
