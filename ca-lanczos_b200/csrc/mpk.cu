@@ -227,7 +227,10 @@ struct PatParam {                          // = calz_mat::h_pat
     unsigned mask[32][8];                  // pattern p: lanes that hold entry k
 };
 
-// NS = 2 consecutive slices per warp and iteration (14 independent gathers in flight for a 7-point stencil).  CNT = number of
+// NS = 2 consecutive slices per warp and iteration (14 independent gathers in flight for a 7-point stencil); items are
+// grid-strided: the whole grid sweeps one narrow window of rows, so the +-plane gathers of a stencil are L2 hits (measured
+// alternative: waves in which every CTA owns 64 consecutive items -- better L1 reuse of the +-line gathers, but 0.83 vs 0.73 ms
+// per C3 MPK).  CNT = number of
 // entries of pattern 0 (compile time: the unrolled loops carry no count tests; values and byte offsets are constant-bank operands
 // of the DFMA / address instructions).  The host only selects this kernel when pattern 0 holds every entry on every lane.
 template <bool NEWTON, int CNT>
@@ -239,15 +242,8 @@ k_spmv_selp(const uint8_t* __restrict__ spat, const int32_t* __restrict__ slice_
     const int lane = threadIdx.x & 31;
     const unsigned lanebit = 1u << lane;
     const int items = (slice_hi - slice_lo + 1) / 2;
-    // Work assignment: the grid advances in WAVES of gridDim.x * 8 * kWaveIters items; inside a wave a CTA owns 8 * kWaveIters
-    // CONSECUTIVE items (4096 rows = 16 grid lines of a 256-wide stencil), one item per warp and iteration.  Consecutive rows per
-    // CTA turn the +-line gathers into L1 hits; the wave keeps the whole grid inside a window of a few MB, so the +-plane gathers
-    // stay L2 hits (a fully contiguous split per CTA would push their reuse distance beyond the L2).
-    constexpr int kWaveIters = 8;
-    constexpr int kWarps = kSpmvThreads / 32;
-    const int warp = threadIdx.x >> 5;
-    const int wave_items = (int)gridDim.x * kWarps * kWaveIters;
-    auto item_of = [&](int c) -> int { return (c / kWaveIters) * wave_items + ((int)blockIdx.x * kWaveIters + c % kWaveIters) * kWarps + warp; };
+    const int stride = (int)gridDim.x * (kSpmvThreads / 32);
+    int it = (int)blockIdx.x * (kSpmvThreads / 32) + (threadIdx.x >> 5);
     auto pids_of = [&](int item) -> int {                 // both pattern numbers of an item in one 16-bit word
         if (item >= items) return 0xffff;
         const int sl = slice_lo + 2 * item;
@@ -255,28 +251,21 @@ k_spmv_selp(const uint8_t* __restrict__ spat, const int32_t* __restrict__ slice_
         const int b = (sl + 1 < slice_hi) ? (int)__ldg(spat + sl + 1) : 254;      // 254: no such slice
         return a | (b << 8);
     };
-    const int niter = ((items + wave_items - 1) / wave_items) * kWaveIters;
-    int pids = pids_of(item_of(0));
-    for (int c = 0; c < niter; ++c) {
-        const int it = item_of(c);
-        const int pids_cur = pids;
-        pids = pids_of(item_of(c + 1));
-        if (it >= items) continue;
+    int pids = pids_of(it);
+    for (; it < items; it += stride) {
+        const int pids_next = pids_of(it + stride);
         const int sl = slice_lo + 2 * it;
         const int row = sl * 32 + lane;
         const char* xr = reinterpret_cast<const char*>(x + row);
         // Of the CNT gathers of a row only the one with the largest offset is new data (a stencil re-reads everything else from
-        // L1/L2), so the gathers in flight cover few DRAM bytes: pull the leading edge of x into L2 `prefetch` iterations ahead.
-        if (prefetch > 0) {
-            const int itp = item_of(c + prefetch);
-            if (itp < items) {
-                const char* pf = reinterpret_cast<const char*>(x + (slice_lo + 2 * itp) * 32 + lane) + PP.e0[CNT - 1].offb;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 256));
-            }
+        // L1/L2), so the gathers in flight cover few DRAM bytes: pull the leading edge of x into L2 kPrefetch iterations ahead.
+        if (prefetch > 0 && it + prefetch * stride < items) {
+            const char* pf = xr + (size_t)prefetch * stride * 512 + PP.e0[CNT - 1].offb;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 256));
         }
         double sum[2] = {0.0, 0.0};
-        if (pids_cur == 0) {
+        if (pids == 0) {
             // two interior slices: every entry on every lane
             double xa[CNT], xb[CNT];
 #pragma unroll
@@ -292,7 +281,7 @@ k_spmv_selp(const uint8_t* __restrict__ spat, const int32_t* __restrict__ slice_
         } else {
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-                const int pid = (pids_cur >> (8 * i)) & 0xff;
+                const int pid = (pids >> (8 * i)) & 0xff;
                 const char* xi = xr + 256 * i;
                 if (pid < 32) {
 #pragma unroll
@@ -318,12 +307,13 @@ k_spmv_selp(const uint8_t* __restrict__ spat, const int32_t* __restrict__ slice_
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const int r = row + 32 * i;
-            if (r < n_loc && ((pids_cur >> (8 * i)) & 0xff) != 254) {
+            if (r < n_loc && ((pids >> (8 * i)) & 0xff) != 254) {
                 double v = sum[i];
                 if (NEWTON) v = newton_epilogue(v, x[r], pair != 0.0 ? xprev[r] : 0.0, shift, pair);
                 y[r] = v;
             }
         }
+        pids = pids_next;
     }
 }
 
