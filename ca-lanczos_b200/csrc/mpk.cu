@@ -283,7 +283,13 @@ k_spmv_selp(const uint8_t* __restrict__ spat, const int32_t* __restrict__ slice_
             for (int i = 0; i < 2; ++i) {
                 const int pid = (pids >> (8 * i)) & 0xff;
                 const char* xi = xr + 256 * i;
-                if (pid < 32) {
+                if (pid == 0) {                                       // interior slice next to a boundary one: no masks
+                    double xa[CNT];
+#pragma unroll
+                    for (int k = 0; k < CNT; ++k) xa[k] = *reinterpret_cast<const double*>(xi + PP.e0[k].offb);
+#pragma unroll
+                    for (int k = 0; k < CNT; ++k) sum[i] = fma(PP.e0[k].v, xa[k], sum[i]);
+                } else if (pid < 32) {
 #pragma unroll
                     for (int k = 0; k < CNT; ++k)
                         if (PP.mask[pid][k] & lanebit) sum[i] = fma(PP.e0[k].v, *reinterpret_cast<const double*>(xi + PP.e0[k].offb), sum[i]);

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--matrix", default="lap3d", choices=["lap3d", "powerlaw"])
     ap.add_argument("--halo-level", type=int, default=0, help="force the ghost-closure depth L (MPK steps per exchange); 0 = automatic")
     ap.add_argument("--own-rows-only", action="store_true", help="supply only the owned rows (forces L = 1, what the C4 bench does)")
+    ap.add_argument("--full-reorth", action="store_true", help="also run the 'fro' driver (second projection against all earlier vectors)")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
@@ -141,6 +142,48 @@ def main():
         w = min(s, Qo.shape[1] - ((k - 1) * s + 1))               # the driver returns Q(:,1:s*t): the last block lacks its last vector
         blk_err = max(blk_err, float(np.max(np.linalg.norm(QZ[:, :w] - Qo[lo:hi, (k - 1) * s + 1:(k - 1) * s + 1 + w], axis=0))))
     check("per-block basis vectors 1e-10", blk_err < 1e-10, "%.3e" % blk_err)
+    # ---- a TWO-block projection whose second pass does NOT fire (the predicated-off branch of the P-rank TSQR/CholQR2 plan):
+    # X = the (ortho)normal columns of the third oracle block, mixed by a well-conditioned matrix, plus a 5 % component in both Q blocks
+    rng = np.random.default_rng(7)
+    Q1o, Q2o = Qo[:, : s + 1], Qo[:, s + 1: 2 * s + 1]
+    Xo = Qo[:, 2 * s + 1: 3 * s + 1] @ (np.eye(s) + 0.1 * rng.standard_normal((s, s))) \
+        + 0.05 * Q1o @ rng.standard_normal((s + 1, s)) + 0.05 * Q2o @ rng.standard_normal((s, s))
+    pinfo = {}
+    QZo, RZo = kernels.projectAndNormalize([Q1o, Q2o], Xo, True, backend="tsqr", info=pinfo)
+    B1 = torch.zeros((s + 1, ld), dtype=torch.float64, device=dev); B2 = torch.zeros((s, ld), dtype=torch.float64, device=dev)
+    Xd = torch.zeros((s, ld), dtype=torch.float64, device=dev); Zd = torch.zeros((s, ld), dtype=torch.float64, device=dev)
+    B1[:, : hi - lo] = torch.as_tensor(np.ascontiguousarray(Q1o[lo:hi].T), device=dev)
+    B2[:, : hi - lo] = torch.as_tensor(np.ascontiguousarray(Q2o[lo:hi].T), device=dev)
+    Xd[:, : hi - lo] = torch.as_tensor(np.ascontiguousarray(Xo[lo:hi].T), device=dev)
+    torch.cuda.synchronize(dev)
+    qb = (C.c_void_p * 2)(B1.data_ptr(), B2.data_ptr()); lds = (C.c_int64 * 2)(ld, ld); mc = (C.c_int * 2)(s + 1, s)
+    Ra = np.zeros((s + 1, s), order="F"); Rb = np.zeros((s, s), order="F"); Rl = np.zeros((s, s), order="F")
+    rp = (_lib.c_dp * 2)(Ra.ctypes.data_as(_lib.c_dp), Rb.ctypes.data_as(_lib.c_dp))
+    sec, rk = C.c_int(), C.c_int()
+    _lib.check(ctx.lib.calz_project_and_normalize(ctx.h, hi - lo, 2, qb, lds, mc, s, C.c_void_p(Xd.data_ptr()), ld, 1,
+                                                  _lib.QR[args.backend], C.c_void_p(Zd.data_ptr()), ld, rp,
+                                                  Rl.ctypes.data_as(_lib.c_dp), C.byref(sec), C.byref(rk)), ctx.h)
+    ctx.sync()
+    check("two-block pan: second pass off on both", (bool(sec.value), pinfo["second_pass"]) == (False, False), "%d %s" % (sec.value, pinfo["second_pass"]))
+    sgn = np.sign(np.diag(Rl)) * np.sign(np.diag(RZo[2]))                  # the reference's R has no sign convention (tsqr.m)
+    e2 = max(float(np.abs(Ra - RZo[0]).max()), float(np.abs(Rb - RZo[1]).max()),
+             float(np.abs(Rl - sgn[:, None] * RZo[2]).max()),
+             float(np.abs(Zd[:, : hi - lo].T.cpu().numpy() - QZo[lo:hi] * sgn[None, :]).max()))
+    check("two-block pan vs oracle 1e-11", e2 < 1e-11, "%.3e" % e2)
+    if args.full_reorth:
+        # 'fro' driver (ca_lanczos.m:193-197) over P ranks: every block is projected a second time against ALL earlier vectors
+        To_f, Qo_f = drivers.ca_lanczos(A, r, s, s * args.blocks, "newton", "full", Bk=io["Bk"])
+        ef = BlockEngine(dm, s, args.blocks + 1, "newton", shifts, args.backend)
+        ef.first_block(q0)
+        for _ in range(args.blocks - 1):
+            ef.next_block(full_reorth=True)
+        Tf = ef.T_matrix(); Qf = ef.Q_host()
+        check("'fro' T 1e-10", np.abs(Tf - To_f).max() <= 1e-10 * np.abs(To_f).max(), "%.3e" % (np.abs(Tf - To_f).max() / np.abs(To_f).max()))
+        efq = np.max(np.linalg.norm(Qf - Qo_f[lo:hi, : Qf.shape[1]], axis=0))
+        check("'fro' Q 1e-10", efq < 1e-10, "%.3e" % efq)
+        from ca_lanczos_b200 import solver
+        of = solver.engine_orth_errors(ef)[1]
+        check("'fro' orthogonality 5e-13", of < 5e-13, "%.3e" % of)
     # MPK alone, through the host flavour with the communicator (owned rows in, owned rows out)
     v = r / np.sqrt(r @ r)
     V = api.matrix_powers_newton(dm, v[lo:hi], s, shifts, 1)

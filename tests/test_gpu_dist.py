@@ -50,3 +50,15 @@ def test_two_rank_multi_exchange_matrix_powers(extra):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
 
+
+
+@pytest.mark.parametrize("backend", ["tsqr", "cholqr2"])
+def test_two_rank_full_reorthogonalisation_and_two_block_projection(backend):
+    # the 'full' driver over 2 ranks (a second projection against ALL earlier vectors per block) and, inside dist_check, a
+    # two-block projectAndNormalize whose second pass does not fire -- the branches a P-rank TSQR plan must keep apart
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29559", os.path.join(ROOT, "tests", "dist_check.py"), "--grid", "32", "--backend", backend, "--full-reorth"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
