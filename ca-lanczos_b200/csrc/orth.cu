@@ -76,6 +76,48 @@ int cholqr_refine(calz_ctx* ctx, int64_t n, int c, double* Q, int64_t ldQ, doubl
     return CALZ_OK;
 }
 
+// ---- projections on the tile kernels for ANY block list (tiles.cu): a block of more than tile_panel_width(c) columns is cut
+// into near-equal column panels; every panel owns a dense (m + c) x c result S = [Q_p Y]'Y per sweep.
+struct PanelRef { int k, a0, m; size_t off1, off2; };         // k: position in the list of non-empty blocks
+void split_panels(int k, int M, int W, std::vector<PanelRef>& out) {
+    const int np = (M + W - 1) / W;
+    for (int p = 0, a0 = 0; p < np; ++p) {
+        const int m = (M - a0 + (np - p) - 1) / (np - p);
+        out.push_back(PanelRef{k, a0, m, 0, 0});
+        a0 += m;
+    }
+}
+
+// One sweep of project.m:32-39, block after block: C_i = Q_i'Y -- one coefficient pass per panel, ALL of them before the block's
+// first update (classical Gram-Schmidt inside a block, modified across blocks, like the reference) -- then Y = Y - Q_i*C_i panel
+// by panel.  The very last update also contracts Y'Y into SG (rows [m_last, m_last + c), leading dimension m_last + c), so the
+// norms-after / the Gram matrix of the following CholQR cost no further pass.  src -> dst on the first update, in place after it.
+int panel_sweep(calz_ctx* ctx, int64_t n, const double* const* Qblk, const int64_t* ldQ, const std::vector<int>& blocks,
+                const std::vector<PanelRef>& panels, int which, int c, const double*& src, int64_t& ldsrc, double* dst, int64_t lddst,
+                double* sm, double* SG, const int* pred, int want) {
+    size_t i = 0;
+    while (i < panels.size()) {
+        size_t j = i;
+        while (j < panels.size() && panels[j].k == panels[i].k) ++j;
+        const int b = blocks[panels[i].k];
+        for (size_t p = i; p < j; ++p) {
+            const PanelRef& P = panels[p];
+            CALZ_TRY(tile_pass(ctx, 0, n, Qblk[b] + (int64_t)P.a0 * ldQ[b], ldQ[b], P.m, src, ldsrc, c, nullptr, 0, nullptr, 0,
+                               sm + (which == 1 ? P.off1 : P.off2), P.m + c, pred, want, true));
+        }
+        for (size_t p = i; p < j; ++p) {
+            const PanelRef& P = panels[p];
+            const bool last = p + 1 == panels.size();
+            CALZ_TRY(tile_pass(ctx, 2, n, Qblk[b] + (int64_t)P.a0 * ldQ[b], ldQ[b], P.m, src, ldsrc, c,
+                               sm + (which == 1 ? P.off1 : P.off2), P.m + c, dst, lddst, last ? SG : nullptr, P.m + c, pred, want, true));
+            src = dst;
+            ldsrc = lddst;
+        }
+        i = j;
+    }
+    return CALZ_OK;
+}
+
 // cholqr.m (single pass) or its CholQR2 variant: R on the host, info = failing pivot (0: none)
 int cholqr_device(calz_ctx* ctx, int64_t n, int c, const double* X, int64_t ldX, double* Q, int64_t ldQ, double* R,
                   int* info, bool adaptive) {
@@ -231,6 +273,50 @@ int calz_project(calz_ctx* ctx, int64_t n, int nblk, const double* const* Qblk, 
                  int c, double* X, int64_t ldX, int doreorth, double* const* Rblk) {
     if (!ctx || !X || n < 1 || c < 1 || c > kMaxC || nblk < 0) return set_error(ctx, CALZ_ERR_BADARG, "calz_project: bad arguments");
     CALZ_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<int> blocks;
+    for (int i = 0; i < nblk; ++i)
+        if (!empty_block(Qblk, mcols, i)) blocks.push_back(i);
+    if (!blocks.empty() && ctx->opt_tile_pipeline && ctx->opt_tile_panels && tile_panel_width(c) > 0) {
+        // ---- tile kernels, panel by panel (shape-only condition: every rank takes the same path).  ||x_i||^2 before comes with the
+        //      first coefficient pass ([Q_p X]'X), the norms after with the last update: no separate Gram passes (project.m:29-31,:41)
+        std::vector<PanelRef> panels;
+        for (size_t k = 0; k < blocks.size(); ++k) split_panels((int)k, mcols[blocks[k]], tile_panel_width(c), panels);
+        size_t doubles = 0;
+        for (PanelRef& P : panels) { P.off1 = doubles; doubles += (size_t)(P.m + c) * c; }
+        for (PanelRef& P : panels) { P.off2 = doubles; doubles += (size_t)(P.m + c) * c; }
+        const int m_last = panels.back().m, ldG = m_last + c;
+        const size_t offSG = doubles; doubles += (size_t)ldG * c;
+        double* sm;
+        CALZ_TRY(small_scratch(ctx, doubles, &sm));
+        CALZ_CUDA(ctx, cudaMemsetAsync(sm, 0, doubles * sizeof(double), ctx->stream));
+        const double* src = X;
+        int64_t ldsrc = ldX;
+        CALZ_TRY(panel_sweep(ctx, n, Qblk, ldQ, blocks, panels, 1, c, src, ldsrc, X, ldX, sm, doreorth ? sm + offSG : nullptr, nullptr, 0));
+        bool second = false;
+        if (doreorth) {
+            CALZ_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, sm, doubles * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            const int ld0 = panels[0].m + c;
+            double worst = -1e300;
+            for (int j = 0; j < c; ++j) {
+                const double b = sqrt(ctx->pinned[panels[0].off1 + (size_t)j * ld0 + panels[0].m + j]);
+                const double a = sqrt(ctx->pinned[offSG + (size_t)j * ldG + m_last + j]);
+                worst = std::max(worst, 0.5 * b - a);
+            }
+            second = worst < 0;             // project.m:43-46, criterion kept as written
+            if (second) CALZ_TRY(panel_sweep(ctx, n, Qblk, ldQ, blocks, panels, 2, c, src, ldsrc, X, ldX, sm, nullptr, nullptr, 0));
+        }
+        CALZ_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, sm, doubles * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CALZ_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        for (const PanelRef& P : panels) {
+            const int i = blocks[P.k], m = mcols[i], ld = P.m + c;
+            if (!Rblk || !Rblk[i]) continue;
+            for (int j = 0; j < c; ++j)
+                for (int a = 0; a < P.m; ++a)
+                    Rblk[i][(size_t)j * m + P.a0 + a] = ctx->pinned[P.off1 + (size_t)j * ld + a] + (second ? ctx->pinned[P.off2 + (size_t)j * ld + a] : 0.0);
+        }
+        return CALZ_OK;
+    }
     size_t tot = 0;
     for (int i = 0; i < nblk; ++i)
         if (!empty_block(Qblk, mcols, i)) tot += (size_t)mcols[i] * c;
@@ -289,8 +375,10 @@ struct PanSlot {
     int64_t n = 0, ldQZ = 0;
     double* QZ = nullptr;
     double* sm = nullptr;            // device scratch base (valid until the next call on the stream reuses it)
-    std::vector<int> blocks, mc, ld1, ld2;
-    std::vector<size_t> off1, off2;
+    std::vector<int> blocks, mc;
+    // where the coefficient pieces live in the scratch: panel p covers rows [a0, a0+m) of block pk[p] (leading dimensions pld1/pld2)
+    std::vector<int> pk, pa0, pm, pld1, pld2;
+    std::vector<size_t> poff1, poff2;
     size_t offRf = 0, offG2 = 0, doubles = 0;
 };
 constexpr int kPanSlots = 8;
@@ -317,18 +405,31 @@ static int pan_enqueue(calz_ctx* ctx, int64_t n, int nblk, const double* const* 
     // tile_path_ok depends on the block shape only (rank-local alignment / row count are handled inside the kernels), so every
     // rank takes the same kernel path and issues the same sequence of collectives
     const bool fused_solve = tiled && backend != CALZ_QR_TSQR && ctx->opt_pan_fused_solve;
+    // every other projection with the norm-drop test (several blocks -- {Qprev, Q_conv} of the restarted driver -- or one wide
+    // block -- 'full' re-orthogonalisation): the same tile kernels, panel by panel.  Shape-only condition, same on all ranks.
+    const bool panelled = !tile_shape && fuse_norms && ctx->opt_tile_pipeline && ctx->opt_tile_panels && tile_panel_width(c) > 0;
     size_t doubles = 8;                                // flags
     std::vector<size_t> off1(nb), off2(nb);
     std::vector<int> ld1(nb), ld2(nb);
-    for (int k = 0; k < nb; ++k) {
-        const int m = mcols[blocks[k]];
-        ld1[k] = (k == 0 && fuse_norms) ? m + c : m;
-        off1[k] = doubles; doubles += (size_t)ld1[k] * c;
+    std::vector<PanelRef> panels;
+    if (panelled) {
+        for (int k = 0; k < nb; ++k) split_panels(k, mcols[blocks[k]], tile_panel_width(c), panels);
+        for (PanelRef& P : panels) { P.off1 = doubles; doubles += (size_t)(P.m + c) * c; }
+        for (PanelRef& P : panels) { P.off2 = doubles; doubles += (size_t)(P.m + c) * c; }
+    } else {
+        for (int k = 0; k < nb; ++k) {
+            const int m = mcols[blocks[k]];
+            ld1[k] = (k == 0 && fuse_norms) ? m + c : m;
+            off1[k] = doubles; doubles += (size_t)ld1[k] * c;
+        }
+        for (int k = 0; k < nb; ++k) {
+            ld2[k] = tiled ? mcols[blocks[k]] + c : mcols[blocks[k]];
+            off2[k] = doubles; doubles += (size_t)ld2[k] * c;
+        }
     }
-    for (int k = 0; k < nb; ++k) {
-        ld2[k] = tiled ? mcols[blocks[k]] + c : mcols[blocks[k]];
-        off2[k] = doubles; doubles += (size_t)ld2[k] * c;
-    }
+    const int m_last = panelled ? panels.back().m : 0;
+    const size_t offSG1 = doubles; doubles += panelled ? (size_t)(m_last + c) * c : 0;     // Gram of Y / of Z from the last update
+    const size_t offSG2 = doubles; doubles += panelled ? (size_t)(m_last + c) * c : 0;
     const size_t offS3 = doubles; doubles += tiled ? (size_t)(mcols[blocks[0]] + c) * c : 0;
     const size_t offG = doubles; doubles += (size_t)c * c;
     const size_t offR1 = doubles; doubles += (size_t)c * c;
@@ -373,6 +474,25 @@ static int pan_enqueue(calz_ctx* ctx, int64_t n, int nblk, const double* const* 
         }
         src = QZ;
         ldsrc = ldQZ;
+    } else if (panelled) {
+        const int ldG = m_last + c;
+        double *SG1 = sm + offSG1, *SG2 = sm + offSG2;
+        // ---- pass 1: Y = X - sum_i Q_i (Q_i'X) into QZ; ||x_i||^2 = diag of the X'X part of the first panel's S; G_Y from the last update
+        CALZ_TRY(panel_sweep(ctx, n, Qblk, ldQ, blocks, panels, 1, c, src, ldsrc, QZ, ldQZ, sm, SG1, nullptr, 0));
+        const double* nb2 = sm + panels[0].off1 + panels[0].m;
+        const int nb2_stride = panels[0].m + c + 1;
+        if (backend != CALZ_QR_TSQR)
+            CALZ_TRY(chol_small(ctx, c, SG1 + m_last, R1, flags + 1, nb2, nb2_stride, flags + 0, nullptr, 0, backend == CALZ_QR_CHOLQR2,
+                                backend == CALZ_QR_CHOLQR2 ? flags + 3 : nullptr, ldG));
+        else
+            CALZ_TRY(norm_drop_from_gram(ctx, c, SG1 + m_last, ldG, nb2, nb2_stride, flags + 0));
+        // ---- pass 2 (iff the norm-drop test fired, projectAndNormalize.m:61-73): Z = Y - sum_i Q_i (Q_i'Y) in place, G_Z
+        CALZ_TRY(panel_sweep(ctx, n, Qblk, ldQ, blocks, panels, 2, c, src, ldsrc, QZ, ldQZ, sm, SG2, flags, 1));
+        if (backend != CALZ_QR_TSQR)
+            CALZ_TRY(chol_small(ctx, c, SG2 + m_last, R2, flags + 2, nullptr, 0, nullptr, flags, 1, backend == CALZ_QR_CHOLQR2,
+                                backend == CALZ_QR_CHOLQR2 ? flags + 4 : nullptr, ldG));
+        else   // one Householder TSQR of whatever QZ holds now (Z, or Y if pass 2 did not fire): the LAST normalize
+            CALZ_TRY(tsqr_factor(ctx, n, c, QZ, ldQZ, R1, nullptr, 0));
     } else {
         // ---- pass 1: Y = X - sum_i Q_i (Q_i' X)   (sequential over blocks, project.m:32-39); Y lives in QZ
         for (int k = 0; k < nb; ++k) {
@@ -413,7 +533,7 @@ static int pan_enqueue(calz_ctx* ctx, int64_t n, int nblk, const double* const* 
         CALZ_TRY(select_r(ctx, c, R1, R2, flags, flags + 3, flags + 4, Rf, flags + 5));
         CALZ_TRY(ts_trsolve(ctx, n, c, src, ldsrc, Rf, QZ, ldQZ, nullptr, 0));
     } else {
-        CALZ_TRY(select_r(ctx, c, R1, tiled ? R1 : R2, flags, nullptr, nullptr, Rf, nullptr));
+        CALZ_TRY(select_r(ctx, c, R1, (tiled || panelled) ? R1 : R2, flags, nullptr, nullptr, Rf, nullptr));
         // the reflectors on the device belong to the last factorisation that actually ran (Y, or Z if pass 2 fired)
         CALZ_TRY(tsqr_form_q(ctx, n, c, src, ldsrc, QZ, ldQZ));
     }
@@ -429,7 +549,19 @@ static int pan_enqueue(calz_ctx* ctx, int64_t n, int nblk, const double* const* 
     CALZ_CUDA(ctx, cudaEventRecord(slot.ev, ctx->stream));
     slot.busy = true;
     slot.nb = nb; slot.c = c; slot.backend = backend; slot.nblk = nblk; slot.n = n; slot.QZ = QZ; slot.ldQZ = ldQZ; slot.sm = sm;
-    slot.blocks = blocks; slot.ld1 = ld1; slot.ld2 = ld2; slot.off1 = off1; slot.off2 = off2;
+    slot.blocks = blocks;
+    slot.pk.clear(); slot.pa0.clear(); slot.pm.clear(); slot.pld1.clear(); slot.pld2.clear(); slot.poff1.clear(); slot.poff2.clear();
+    if (panelled) {
+        for (const PanelRef& P : panels) {
+            slot.pk.push_back(P.k); slot.pa0.push_back(P.a0); slot.pm.push_back(P.m);
+            slot.pld1.push_back(P.m + c); slot.pld2.push_back(P.m + c); slot.poff1.push_back(P.off1); slot.poff2.push_back(P.off2);
+        }
+    } else {
+        for (int k = 0; k < nb; ++k) {
+            slot.pk.push_back(k); slot.pa0.push_back(0); slot.pm.push_back(mcols[blocks[k]]);
+            slot.pld1.push_back(ld1[k]); slot.pld2.push_back(ld2[k]); slot.poff1.push_back(off1[k]); slot.poff2.push_back(off2[k]);
+        }
+    }
     slot.mc.assign(nblk, 0);
     for (int i = 0; i < nblk; ++i) slot.mc[i] = empty_block(Qblk, mcols, i) ? 0 : mcols[i];
     slot.offRf = offRf; slot.offG2 = offG2; slot.doubles = doubles;
@@ -461,14 +593,15 @@ static int pan_finish(calz_ctx* ctx, PanSlot& slot, double* const* Rblk, double*
         }
     }
     if (second_pass) *second_pass = second ? 1 : 0;
-    for (int k = 0; k < nb; ++k) {
-        const int i = slot.blocks[k], m = slot.mc[i];
+    (void)nb;
+    for (size_t p = 0; p < slot.pk.size(); ++p) {
+        const int i = slot.blocks[slot.pk[p]], m = slot.mc[i], a0 = slot.pa0[p];
         if (!Rblk || !Rblk[i]) continue;
         for (int j = 0; j < c; ++j)
-            for (int a = 0; a < m; ++a) {
-                double v = h[slot.off1[k] + (size_t)j * slot.ld1[k] + a];
-                if (second) v = h[slot.off2[k] + (size_t)j * slot.ld2[k] + a] + v;      // RZ{i} = RZ{i} + RY{i}  (:71-73)
-                Rblk[i][(size_t)j * m + a] = v;
+            for (int a = 0; a < slot.pm[p]; ++a) {
+                double v = h[slot.poff1[p] + (size_t)j * slot.pld1[p] + a];
+                if (second) v = h[slot.poff2[p] + (size_t)j * slot.pld2[p] + a] + v;    // RZ{i} = RZ{i} + RY{i}  (:71-73)
+                Rblk[i][(size_t)j * m + a0 + a] = v;
             }
     }
     const double* Rl = h + slot.offRf;

@@ -273,7 +273,8 @@ k_tile(TileArgs p, int stages) {
                     }
                 }
             }
-            // ---- contraction over the 16 rows of this warp: S += [Q Y]' Y
+            // ---- contraction over the 16 rows of this warp: S += [Q Y]' Y   (skipped when the caller wants no S: a pure update)
+            if (p.partials)
 #pragma unroll
             for (int u = 0; u < (SOLVE ? 0 : 4); ++u) {
                 const int row = 16 * warp + 4 * u + tq;
@@ -305,7 +306,7 @@ k_tile(TileArgs p, int stages) {
                 tile[g * 8 + 2 * tq + 1] = acc[a][b][1];
             }
     }
-    if (SOLVE) return;
+    if (SOLVE || !p.partials) return;
     __syncthreads();
     constexpr int ELEMS = NRT * CT * 64;
     double* out = p.partials + (size_t)blockIdx.x * ELEMS;
@@ -436,6 +437,10 @@ int launch_tile(calz_ctx* ctx, const TileArgs& a0, bool fuse_allreduce = false) 
     const size_t budget = ((size_t)sm_max - 2 * 1024) / 2 - 512;
     int stages = 4;
     while (stages > 2 && fixed + stages * stage_bytes > budget) --stages;
+    if (fixed + stages * stage_bytes > budget) {         // wide panels: one CTA per SM with as deep a ring as fits
+        stages = 4;
+        while (stages > 2 && fixed + stages * stage_bytes > (size_t)dev_max) --stages;
+    }
     const size_t smem = fixed + stages * stage_bytes;
     if (smem > (size_t)dev_max) return set_error(ctx, CALZ_ERR_UNSUPPORTED, "tile kernel needs %zu B of shared memory", smem);
     auto kern = k_tile<MT, CT, MODE>;
@@ -445,14 +450,16 @@ int launch_tile(calz_ctx* ctx, const TileArgs& a0, bool fuse_allreduce = false) 
     per_sm = std::min(per_sm, 2);
     const long long ntiles = (a.n + kTileRows - 1) / kTileRows;
     const int grid = (int)std::max<long long>(1, std::min<long long>((long long)ctx->num_sms * per_sm, ntiles));
-    if (!SOLVE) {
+    const bool want_S = !SOLVE && a.S != nullptr;
+    a.partials = nullptr;
+    if (want_S) {
         CALZ_TRY(reserve(ctx, ctx->partials, (size_t)grid * NRT * CT * 64 * sizeof(double)));
         a.partials = (double*)ctx->partials.p;
     }
     a.ticket = ctx->ticket;
     kern<<<grid, kTileThreads, smem, ctx->stream>>>(a, stages);
     CALZ_LAUNCH_CHECK(ctx);
-    if (SOLVE) return CALZ_OK;
+    if (!want_S) return CALZ_OK;
     ArArgs ar{};
     ar.P = 1;
     if (fuse_allreduce) p2p_next_allreduce(ctx, &ar);
@@ -472,6 +479,8 @@ bool tile_path_ok(int64_t n, const double* Q, int64_t ldQ, int M, const double* 
     (void)Q; (void)ldQ; (void)X; (void)ldX; (void)Y; (void)ldY;
     return n >= 1 && M >= 1 && M <= 16 && c >= 1 && c <= 16;
 }
+// widest panel of Q one tile pass takes against a block of c columns (shared memory: 8*(MT+CT) column slots per stage)
+int tile_panel_width(int c) { return c <= 8 ? 48 : (c <= 16 ? 32 : 0); }
 static int tile_use_tma(const TileArgs& a) { return aligned16(a.Q, a.ldQ) && aligned16(a.X, a.ldX) ? 1 : 0; }
 
 // mode: 0 = COEFF (S = [Q X]'X), 1 = UPDATE_FULL (Y = X - Q*C, S = [Q Y]'Y), 2 = UPDATE_GRAM (Y = X - Q*C, S rows [M,M+c) = Y'Y)
@@ -482,22 +491,35 @@ int tile_pass(calz_ctx* ctx, int mode, int64_t n, const double* Q, int64_t ldQ, 
     a.S = S_dev; a.ldS = ldS; a.pred = pred; a.want = want;
     a.use_tma = tile_use_tma(a);
     const int MT = (M + 7) / 8, CT = (c + 7) / 8;
+    if (M < 1 || c < 1 || CT > 2 || M > tile_panel_width(c) || (mode == 1 && MT > 2))
+        return set_error(ctx, CALZ_ERR_BADARG, "tile_pass: panel of %d columns against a block of %d", M, c);
     int st;
+    const bool want_S = S_dev != nullptr;
     // with a communicator and the peer-memory mailbox available the finalize launch is the all-reduce too.  Not for a predicated
     // pass: a skipped launch would leave the peers waiting (the generic all-reduce below always runs).
-    const bool fuse_ar = allreduce && ctx->nranks > 1 && !pred && ldS == M + c && p2p_allreduce_ok(ctx, (size_t)ldS * c) &&
+    const bool fuse_ar = want_S && allreduce && ctx->nranks > 1 && !pred && ldS == M + c && p2p_allreduce_ok(ctx, (size_t)ldS * c) &&
                          ctx->opt_fused_allreduce;
 #define CALZ_TILE(MTv, CTv)                                                         \
     st = mode == 0 ? launch_tile<MTv, CTv, MODE_COEFF>(ctx, a, fuse_ar)             \
        : mode == 1 ? launch_tile<MTv, CTv, MODE_UPDATE_FULL>(ctx, a, fuse_ar)       \
                    : launch_tile<MTv, CTv, MODE_UPDATE_GRAM>(ctx, a, fuse_ar)
+    // wide panels (multi-block projections, 'full' re-orthogonalisation): coefficient and update+Gram passes only
+#define CALZ_TILE_WIDE(MTv, CTv)                                                    \
+    st = mode == 0 ? launch_tile<MTv, CTv, MODE_COEFF>(ctx, a, fuse_ar)             \
+                   : launch_tile<MTv, CTv, MODE_UPDATE_GRAM>(ctx, a, fuse_ar)
     if (MT == 1 && CT == 1) { CALZ_TILE(1, 1); }
     else if (MT == 2 && CT == 1) { CALZ_TILE(2, 1); }
     else if (MT == 1 && CT == 2) { CALZ_TILE(1, 2); }
-    else { CALZ_TILE(2, 2); }
+    else if (MT == 2 && CT == 2) { CALZ_TILE(2, 2); }
+    else if (CT == 1) {
+        if (MT == 3) { CALZ_TILE_WIDE(3, 1); } else if (MT == 4) { CALZ_TILE_WIDE(4, 1); } else { CALZ_TILE_WIDE(6, 1); }
+    } else {
+        if (MT == 3) { CALZ_TILE_WIDE(3, 2); } else { CALZ_TILE_WIDE(4, 2); }
+    }
+#undef CALZ_TILE_WIDE
 #undef CALZ_TILE
     CALZ_TRY(st);
-    if (allreduce && ctx->nranks > 1 && !fuse_ar) {
+    if (want_S && allreduce && ctx->nranks > 1 && !fuse_ar) {
         // a predicated-off pass leaves S untouched on every rank alike, so the collective stays consistent
         if (mode == 2) {
             if (ldS != M + c) return set_error(ctx, CALZ_ERR_BADARG, "tile_pass: dense S expected");

@@ -60,6 +60,8 @@ int tile_update_solve(calz_ctx* ctx, int64_t n, const double* Q, int64_t ldQ, in
 
 // fused TMA-tile passes of projectAndNormalize (tiles.cu)
 bool tile_path_ok(int64_t n, const double* Q, int64_t ldQ, int M, const double* X, int64_t ldX, int c, const double* Y, int64_t ldY);
+int tile_panel_width(int c);        // widest Q panel per pass (0: the block is too wide for the tile kernels)
+// S_dev == NULL (update modes): a pure update, nothing contracted.  Panels wider than 16 columns: modes 0 and 2 only.
 int tile_pass(calz_ctx* ctx, int mode, int64_t n, const double* Q, int64_t ldQ, int M, const double* X, int64_t ldX, int c,
               const double* C_dev, int ldC, double* Y, int64_t ldY, double* S_dev, int ldS, const int* pred, int want, bool allreduce);
 

@@ -148,7 +148,8 @@ def test_project_doreorth_branch():
 
 
 @pytest.mark.parametrize("backend", ["cholqr", "tsqr", "cholqr2"])
-@pytest.mark.parametrize("n,ms,c", [(6000, [5], 4), (50000, [9], 8), (4000, [9, 12], 8), (3000, [], 5), (3000, [0], 5), (7000, [17], 16)])
+@pytest.mark.parametrize("n,ms,c", [(6000, [5], 4), (50000, [9], 8), (4000, [9, 12], 8), (3000, [], 5), (3000, [0], 5), (7000, [17], 16),
+                                    (5000, [100], 8), (4000, [7, 10], 6), (3000, [40, 33], 16), (2000, [49], 8), (1500, [12], 20)])
 def test_project_and_normalize(backend, n, ms, c):
     Q = []
     for i, m in enumerate(ms):
@@ -173,12 +174,45 @@ def test_project_and_normalize(backend, n, ms, c):
             assert (r is None) == (ro is None)
             if r is not None:
                 assert rel(r, ro) < tolR
-        assert rel(QZ, QZo) < tolR
+        # two backward-stable projections of a block that cancels by ||X||/||Y|| differ by that factor times eps in Y, and the
+        # orthonormal factor of an ill-conditioned Y (tall_skinny grows kappa with c) by kappa times that
+        amp = np.linalg.norm(X) / np.linalg.norm(RZo[-1])
+        assert rel(QZ, QZo) < max(tolR, 10 * kappa * amp * EPS)
         rec = sum((q @ r for q, r in zip(Q, RZ) if q is not None), np.zeros_like(X)) + QZ @ RZ[-1]
         assert rel(rec, X) < 1e-13                                 # reconstruction identity (Appendix B)
         assert orth(QZ) <= max(10 * orth(QZo), 1e-13)              # orthogonality no worse than the oracle
         for q in real:
             assert np.linalg.norm(q.T @ QZ) < 1e-11
+
+
+@pytest.mark.parametrize("backend", ["cholqr2", "tsqr"])
+@pytest.mark.parametrize("n,ms,c", [(30000, [49], 8), (9000, [7, 10], 6), (5000, [33, 40], 12), (777, [97], 3)])
+def test_panelled_projection_matches_legacy_kernels(backend, n, ms, c):
+    # several blocks / one wide block: the tile kernels panel by panel (default) against the legacy Gram + update kernels
+    Q = []
+    for i, m in enumerate(ms):
+        Q.append(kernels.tsqr(kernels.project(Q, gallery.tall_skinny(n, m, seed=300 + i))[0])[0])
+    ctx = api.default_context()
+    for X in (gallery.tall_skinny(n, c, seed=11), Q[0][:, :1] @ np.ones((1, c)) + 1e-3 * gallery.tall_skinny(n, c, seed=12)):
+        out = {}
+        for opt in (1, 0):
+            ctx.set_option("tile_panels", opt)
+            info = {}
+            try:
+                QZ, RZ = api.projectAndNormalize(Q, X, True, backend=backend, info=info)
+                Y, RY = api.project(Q, X, True)
+            finally:
+                ctx.set_option("tile_panels", 1)
+            out[opt] = (QZ, RZ, info["second_pass"], Y, RY)
+        assert out[1][2] == out[0][2]
+        sgn = np.sign(np.diag(out[1][1][-1])) * np.sign(np.diag(out[0][1][-1]))
+        assert rel(out[1][0] * sgn[None, :], out[0][0]) < 1e-11
+        for r1, r0 in zip(out[1][1][:-1], out[0][1][:-1]):
+            assert rel(r1, r0) < 1e-12
+        assert rel(out[1][1][-1] * sgn[:, None], out[0][1][-1]) < 1e-11
+        assert np.linalg.norm(out[1][3] - out[0][3]) <= 1e-13 * np.linalg.norm(X)
+        for r1, r0 in zip(out[1][4], out[0][4]):
+            assert rel(r1, r0) < 1e-12
 
 
 @pytest.mark.parametrize("backend", ["cholqr", "cholqr2"])
