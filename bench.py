@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-sell-ref", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-clocks", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=VALUE", help="library option (calz_set_option), repeatable")
     ap.add_argument("--no-parity", action="store_true", help="skip the untimed small-grid comparison with the CPU oracle")
     ap.add_argument("--sync-blocks", action="store_true", help="one host synchronisation per block (no pipelining)")
     ap.add_argument("--lag", type=int, default=3, help="projectAndNormalize calls in flight in the pipelined loop")
@@ -300,6 +301,8 @@ def run_b200(args):
         dist.broadcast_object_list(ids, src=0)
         ctx.init_comm(world, rank, ids[0])
     ctx.set_option("mpk_l2_chunk_bytes", args.l2_chunk_mb << 20)
+    for kv in args.opt:
+        ctx.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     parity = None if args.no_parity else parity_check(args, torch, dist, ctx, world, rank, dev)
 

@@ -98,6 +98,7 @@ struct calz_ctx {
     int64_t opt_fused_allreduce = 1; // tile passes: the finalize launch is the peer-memory all-reduce as well
     int64_t opt_p2p = 1;             // peer-memory all-reduce / halo push instead of NCCL (when IPC works)
     calz::P2P p2p;
+    int64_t opt_mpk_pair_phase = -1; // slice pairing of the pattern kernel: -1 = the matrix' own choice, 0 / 1 forced (tests)
     int64_t opt_tile_panels = 1;     // tile kernels for multi-block / wide-block projections too, panel by panel (0: legacy kernels)
     int64_t opt_tile_pipeline = 1;   // fused TMA-tile passes in projectAndNormalize (0: legacy kernels)
     int64_t opt_grid_mult = 8;       // CTAs per SM for the persistent tall-skinny kernels

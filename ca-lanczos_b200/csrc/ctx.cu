@@ -253,6 +253,7 @@ int calz_set_option(calz_ctx* ctx, const char* key, int64_t value) {
     else if (!strcmp(key, "mpk_xs_rows")) ctx->opt_mpk_xs_rows = value;
     else if (!strcmp(key, "tile_pipeline")) ctx->opt_tile_pipeline = value;
     else if (!strcmp(key, "tile_panels")) ctx->opt_tile_panels = value;
+    else if (!strcmp(key, "mpk_pair_phase")) ctx->opt_mpk_pair_phase = value;
     else if (!strcmp(key, "grid_mult")) ctx->opt_grid_mult = value > 0 ? value : 1;
     else return set_error(ctx, CALZ_ERR_BADARG, "calz_set_option: unknown key '%s'", key);
     return CALZ_OK;

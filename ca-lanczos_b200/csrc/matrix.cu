@@ -597,6 +597,13 @@ int calz_mat_create_csr(calz_ctx* ctx, int64_t n_glob, int64_t row_begin, int64_
                     if (prov[sl] >= 0 && newid[prov[sl]] >= 0) { spat[sl] = (uint8_t)newid[prov[sl]]; ++covered; }
             }
             m->pat_cover = m->sell_slices ? (double)covered / (double)m->sell_slices : 0.0;
+            {   // pairing phase: the one with more all-interior pairs (both slices of the item carry pattern 0)
+                int64_t cnt[2] = {0, 0};
+                for (int ph = 0; ph < 2; ++ph)
+                    for (int64_t sl = -ph; sl + 1 < m->sell_slices; sl += 2)
+                        if (sl >= 0 && spat[sl] == 0 && spat[sl + 1] == 0) ++cnt[ph];
+                m->pat_phase = cnt[1] > cnt[0] ? 1 : 0;
+            }
             CALZ_TRY(upload(ctx, &m->d_slice_pat, spat));
         }
         m->sell_padded = blocks * 256;
@@ -754,6 +761,7 @@ int calz_mat_info(const calz_mat* m, const char* what, int64_t* value) {
     else if (!strcmp(what, "dict_size")) *value = m->dict_size;
     else if (!strcmp(what, "dict_uniform_pct")) *value = (int64_t)(100.0 * m->dict_uniform);
     else if (!strcmp(what, "n_patterns")) *value = m->n_pat;
+    else if (!strcmp(what, "pattern_pair_phase")) *value = m->pat_phase;
     else if (!strcmp(what, "pattern_cover_pct")) *value = (int64_t)(100.0 * m->pat_cover);
     else if (!strcmp(what, "xs_rows")) *value = m->xs_rows;
     else if (!strcmp(what, "xs_groups")) *value = m->xs_groups;

@@ -74,6 +74,7 @@ struct calz_mat {
     struct { HostPatEnt e0[8]; unsigned mask[32][8]; } h_pat[1] = {};
     int n_pat = 0;
     int pat_cnt0 = 0;                                 // entries of pattern 0; 0: no usable pattern 0 (it must cover all 32 lanes)
+    int pat_phase = 0;                                // slice pairing of k_spmv_selp: items are slices (2j - phase, 2j - phase + 1)
     double pat_cover = 0.0;                           // fraction of the slices that have a pattern
     uint8_t* d_slice_pat = nullptr;                   // per slice: pattern number, 255 = none (coded path)
     // ... and its TMA-staged kernel: x segments of a CTA's row block (merged over overlapping offsets)

@@ -238,29 +238,47 @@ __global__ void __launch_bounds__(kSpmvThreads, 5)
 k_spmv_selp(const uint8_t* __restrict__ spat, const int32_t* __restrict__ slice_ptr, const uint2* __restrict__ codes,
             const __grid_constant__ DictParam D, const __grid_constant__ PatParam PP, const double* __restrict__ x,
             const double* __restrict__ xprev, double* __restrict__ y, int slice_lo, int slice_hi, int n_loc, double shift, double pair,
-            int prefetch) {
+            int prefetch, int phase) {
     const int lane = threadIdx.x & 31;
     const unsigned lanebit = 1u << lane;
-    const int items = (slice_hi - slice_lo + 1) / 2;
+    // item j (absolute) = slices 2j - phase and 2j - phase + 1.  phase (0/1, chosen per matrix at set-up) is the pairing that puts
+    // most slices with a boundary pattern TOGETHER -- a 256-row grid line is 8 slices whose first and last one touch the boundary:
+    // paired (7 | 0 of the next line) three items of four take the interior fast path, paired (0 1) ... (6 7) only two of four do.
+    const int j0 = (slice_lo + phase) >> 1, items = ((slice_hi - 1 + phase) >> 1) - j0 + 1;
     const int stride = (int)gridDim.x * (kSpmvThreads / 32);
-    int it = (int)blockIdx.x * (kSpmvThreads / 32) + (threadIdx.x >> 5);
+    const int wid = (int)blockIdx.x * (kSpmvThreads / 32) + (threadIdx.x >> 5);
+    // Round k of the grid sweep covers items [k*stride, (k+1)*stride); inside a round the warps ROTATE by one item per round
+    // (warp w takes item k*stride + (w + k) mod stride).  stride is a multiple of 8 and so is the period of the boundary slices of
+    // a power-of-two grid line: without the rotation a warp would meet the same kind of item (all interior, or all boundary) in
+    // every round and the boundary warps would finish last.
+    auto item_of = [&](int k) -> int {
+        int r = wid + k;
+        if (r >= stride) r -= stride;
+        return k * stride + r;
+    };
+    int k = 0;
+    int it = item_of(0);
     auto pids_of = [&](int item) -> int {                 // both pattern numbers of an item in one 16-bit word
         if (item >= items) return 0xffff;
-        const int sl = slice_lo + 2 * item;
-        const int a = (int)__ldg(spat + sl);
-        const int b = (sl + 1 < slice_hi) ? (int)__ldg(spat + sl + 1) : 254;      // 254: no such slice
+        const int sl = 2 * (j0 + item) - phase;
+        const int a = (sl >= slice_lo) ? (int)__ldg(spat + sl) : 254;             // 254: no such slice in this launch
+        const int b = (sl + 1 < slice_hi) ? (int)__ldg(spat + sl + 1) : 254;
         return a | (b << 8);
     };
     int pids = pids_of(it);
-    for (; it < items; it += stride) {
-        const int pids_next = pids_of(it + stride);
-        const int sl = slice_lo + 2 * it;
+    const int pf_items = prefetch * stride;
+    const long long pf_off = (long long)pf_items * 512 + PP.e0[CNT - 1].offb;
+    for (; k * stride < items; ++k) {
+        const int it_next = item_of(k + 1);
+        const int pids_next = pids_of(it_next);
+        if (it >= items) { it = it_next; pids = pids_next; continue; }      // only in the last, partial round
+        const int sl = 2 * (j0 + it) - phase;
         const int row = sl * 32 + lane;
         const char* xr = reinterpret_cast<const char*>(x + row);
         // Of the CNT gathers of a row only the one with the largest offset is new data (a stencil re-reads everything else from
         // L1/L2), so the gathers in flight cover few DRAM bytes: pull the leading edge of x into L2 kPrefetch iterations ahead.
-        if (prefetch > 0 && it + prefetch * stride < items) {
-            const char* pf = xr + (size_t)prefetch * stride * 512 + PP.e0[CNT - 1].offb;
+        if (prefetch > 0 && it + pf_items < items) {
+            const char* pf = xr + pf_off;
             asm volatile("prefetch.global.L2 [%0];" ::"l"(pf));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 256));
         }
@@ -320,6 +338,7 @@ k_spmv_selp(const uint8_t* __restrict__ spat, const int32_t* __restrict__ slice_
             }
         }
         pids = pids_next;
+        it = it_next;
     }
 }
 
@@ -333,11 +352,12 @@ int launch_selp_t(calz_mat* m, const double* x, const double* xp, double* y, int
         if (occ < 1) occ = 1;
     }
     const int64_t per_cta = 2 * (kSpmvThreads / 32);
-    const unsigned grid = (unsigned)std::min<int64_t>((s1 - s0 + per_cta - 1) / per_cta, (int64_t)ctx->num_sms * occ);
+    const unsigned grid = (unsigned)std::min<int64_t>((s1 - s0 + 1 + per_cta - 1) / per_cta, (int64_t)ctx->num_sms * occ);
     static_assert(sizeof(PatParam) == sizeof(m->h_pat), "pattern parameter block");
     k_spmv_selp<NEWTON, CNT><<<grid, kSpmvThreads, 0, ctx->stream>>>(m->d_slice_pat, m->d_slice_ptr, (const uint2*)m->d_codes,
                                                                       *(const DictParam*)m->h_dict, *(const PatParam*)m->h_pat, x, xp, y,
-                                                                      (int)s0, (int)s1, (int)m->n_loc, shift, pair, (int)ctx->opt_mpk_prefetch);
+                                                                      (int)s0, (int)s1, (int)m->n_loc, shift, pair, (int)ctx->opt_mpk_prefetch,
+                                                                      ctx->opt_mpk_pair_phase < 0 ? m->pat_phase : (int)(ctx->opt_mpk_pair_phase & 1));
     CALZ_LAUNCH_CHECK(ctx);
     return CALZ_OK;
 }

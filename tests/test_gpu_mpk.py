@@ -185,13 +185,39 @@ def test_slice_patterns_of_a_stencil():
     dm = api.DeviceMatrix(A, 4, "selld")
     assert 1 <= dm.info("n_patterns") <= 32
     assert dm.info("pattern_cover_pct") >= 99
+    assert dm.info("pattern_pair_phase") in (0, 1)
     try:
         for prefetch in (1, 0, 8):                                 # several L2 prefetch distances
-            ctx.set_option("mpk_prefetch", prefetch)
-            np.testing.assert_array_equal(api.matrix_powers_newton(dm, v, 4, lam, 1), ref[0])
-            np.testing.assert_array_equal(api.matrix_powers_monomial(dm, v, 3), ref[1])
+            for phase in (-1, 0, 1):                               # the matrix' own slice pairing, and both forced ones
+                ctx.set_option("mpk_prefetch", prefetch)
+                ctx.set_option("mpk_pair_phase", phase)
+                np.testing.assert_array_equal(api.matrix_powers_newton(dm, v, 4, lam, 1), ref[0])
+                np.testing.assert_array_equal(api.matrix_powers_monomial(dm, v, 3), ref[1])
     finally:
         ctx.set_option("mpk_prefetch", 1)
+        ctx.set_option("mpk_pair_phase", -1)
+        dm.close()
+
+
+def test_slice_pairing_phase_of_a_256_wide_grid():
+    # 8 slices per grid line, the first and the last one touch the x boundary: pairing (7 | 0 of the next line) keeps three items
+    # of four on the interior path -- the set-up must pick phase 1; odd slice counts and both phases give the same bits as plain SELL
+    A = gallery.laplace3d(256, 6, 5)
+    n = A.shape[0]
+    v = np.sin(0.07 * np.arange(n)) + 0.2
+    lam = np.array([4.0, 1.0, 2.5])
+    ctx = api.default_context()
+    ref_dm = api.DeviceMatrix(A, 3, "sell")
+    ref = api.matrix_powers_newton(ref_dm, v, 3, lam, 1)
+    ref_dm.close()
+    dm = api.DeviceMatrix(A, 3, "selld")
+    try:
+        assert dm.info("pattern_pair_phase") == 1
+        for phase in (-1, 0, 1):
+            ctx.set_option("mpk_pair_phase", phase)
+            np.testing.assert_array_equal(api.matrix_powers_newton(dm, v, 3, lam, 1), ref)
+    finally:
+        ctx.set_option("mpk_pair_phase", -1)
         dm.close()
 
 
