@@ -64,8 +64,10 @@ void* calz_get_stream(calz_ctx* ctx);
 int  calz_sync(calz_ctx* ctx);
 /* number of kernels launched by this library since the last reset (bench.py "gpu_launches") */
 int64_t calz_launch_count(calz_ctx* ctx, int reset);
-/* knobs: "mpk_l2_chunk_bytes" (0 = no temporal blocking), "sell_sigma", "csr_lanes", "grid_mult",
- * "cholqr2_inv_thresh" (second pass when min_j R_jj/||x_j|| < 1/value; default 32) */
+/* knobs (INTEGRATION.md has the table with defaults): "mpk_patterns", "mpk_prefetch", "mpk_pair_phase", "mpk_halo_level",
+ * "mpk_dict_mode", "mpk_persist", "mpk_tma_x", "mpk_l2_chunk_bytes", "mpk_fused_steps", "sell_dict", "sell_sigma", "csr_lanes",
+ * "grid_mult", "tile_pipeline", "tile_panels", "pan_fused_solve", "fused_allreduce", "p2p",
+ * "cholqr2_inv_thresh" (second pass when min_j R_jj/||x_j|| < 1/value; default 32).  Unknown key: CALZ_ERR_BADARG. */
 int  calz_set_option(calz_ctx* ctx, const char* key, int64_t value);
 
 /* ------------------------------------------------------------------ process-wide state (MEX gateways) -- */
