@@ -62,7 +62,7 @@ def parse():
                          "(s=6, TSQR); c5: TSQR vs CholQR sweep on n x (s+1) blocks -- c4/c5 are extra lines kept under profiles/")
     ap.add_argument("--size", dest="n", type=int, default=0,
                     help="c4: matrix order (default 2e7); c5: total rows (default 1e8)  [not --n: torchrun prefix-matches its own options]")
-    ap.add_argument("--orth", default="full", choices=["local", "full"],
+    ap.add_argument("--orth", default="full", choices=["local", "full", "periodic", "selective"],
                     help="c4: orthogonalisation of restarted_ca_lanczos ('local' is the reference default; on this matrix it loses "
                          "orthogonality within the first cycle in the reference as well -- see DESIGN.md)")
     ap.add_argument("--shifts", default="reference", choices=["reference", "chebyshev"],

@@ -1,6 +1,7 @@
 """Device-resident ``restarted_ca_lanczos``: the reference's restarted driver with every O(n) operation
 behind a small *block-operations* object, so that the basis, the converged Ritz vectors and the restart vector never leave
-the GPU (restarted_ca_lanczos.m:4-202 'local' and 'full'; lanczos_basic :288-367; generateStartVector 'largest' :204-248).
+the GPU (restarted_ca_lanczos.m:4-202, all four orth modes: lanczos_basic 'local'/'full' :288-367, lanczos_selective :369-463,
+lanczos_periodic :465-552; generateStartVector 'largest' :204-248).
 
     eigs, Qconv, nrestarts, rnorms, orth_err = restarted_ca_lanczos(ops, r, max_lanczos, n_wanted_eigs, s, basis, orth, tol)
 
@@ -127,15 +128,97 @@ def _lanczos_basic(ops, Qc, q, Bk, maxiter, s, basis, orth, Q):
     return np.asfortranarray(T[:s * maxiter + 1, :s * maxiter])                        # :365-366
 
 
+def _restarted_periodic_reorth_needed(omega, k, s):
+    """restarted_ca_lanczos.m:535-543: row maximum over the first i entries only, no abs(), threshold sqrt(eps/(k*s)) -- as written
+    (the non-restarted driver's test, ca_lanczos.m:437-446, is a different one)."""
+    err = 0.0
+    for i in range(1, s + 1):
+        row_err = float(np.max(omega[(k - 1) * s + i, :i]))
+        if row_err > err:
+            err = row_err
+    return err >= np.sqrt(np.finfo(np.float64).eps / (k * s))
+
+
+def _lanczos_periodic_selective(ops, Qc, q, Bk, maxiter, s, basis, orth, Q, norm_A, log=None):
+    """lanczos_selective (restarted_ca_lanczos.m:369-463) and lanczos_periodic (:465-552) over the block operations: maxiter+1
+    blocks (``while k <= maxiter``), every block projected against {Qprev, Q_conv} (:500) or {Qprev, Q_conv, QR(:,1:nritz)}
+    (:405); periodic: the omega recurrence on the host (:532-534) and, when it trips, the s+1 newest vectors re-orthogonalised
+    against everything before them (:544); selective: eig of the current T, Ritz vectors whose estimated residual fell below
+    ||A|| sqrt(eps) are formed, orthonormalised (:444-454) and joined to the projection list."""
+    from .solver import reset_omega, update_omega
+    nblk = maxiter + 1
+    b = np.zeros(nblk + 1)
+    T = None
+    tmp = ops.block(s + 1)
+    omega = None
+    nritz, breaks = 0, []
+    QRraw = QRo = None
+    eps = np.finfo(np.float64).eps
+    for k in range(1, nblk + 1):
+        qk = q if k == 1 else ops.view(Q, (k - 1) * s, (k - 1) * s + 1)
+        V = ops.matrix_powers(qk, s, Bk, basis)
+        if k == 1:
+            Rk = ops.normalize(V, tmp)                                                 # :394 / :489
+            ops.pan([Qc], tmp, ops.view(Q, 0, s + 1))                                  # :396 / :491
+            T = _solve_upper_right(Rk @ Bk, Rk[:s, :s])
+            b[0] = T[s, s - 1]
+        else:
+            blocks = [ops.view(Q, (k - 2) * s, (k - 1) * s + 1), Qc]
+            if orth == "selective":
+                blocks.append(ops.view(QRo, 0, nritz) if nritz > 0 else None)
+            R = ops.pan(blocks, ops.view(V, 1, s + 1), ops.view(Q, (k - 1) * s + 1, k * s + 1))
+            T = _extend_T(T, b, k, s, Bk, R[0], R[-1])                                 # Rk_{1}, Rk_{3} / Rk_{4}
+        if orth == "periodic":
+            omega = update_omega(omega, np.diag(T, 0).copy(), np.diag(T, -1).copy(), norm_A, s)
+            if _restarted_periodic_reorth_needed(omega, k, s):
+                breaks.append(k)
+                old = ops.view(Q, 0, (k - 1) * s) if (k - 1) * s > 0 else None
+                cur = ops.view(Q, (k - 1) * s, k * s + 1)
+                ops.pan([old], cur, tmp)                                               # :544 (QZ may not alias X: through tmp)
+                ops.axpy(tmp, -np.eye(s + 1), None, cur)
+                omega = reset_omega(omega, norm_A, s)
+        else:
+            m = s * k
+            _, Vp = np.linalg.eig(T[:m, :m])                                           # :436
+            Vp = np.real(Vp)
+            conv = b[k - 1] * np.abs(Vp[m - 1, :]) < norm_A * np.sqrt(eps)             # :438-443
+            if int(conv.sum()) > nritz:                                                # :444-454
+                breaks.append(k)
+                nritz = int(conv.sum())
+                if QRraw is None:
+                    QRraw, QRo = ops.block(nblk * s), ops.block(nblk * s)
+                cols = np.flatnonzero(conv)
+                Qm = ops.view(Q, 0, m)
+                for c0 in range(0, nritz, 16):                                         # y = Q(:,1:k*s)*Vp(:,i), 16 columns a call
+                    cc = min(16, nritz - c0)
+                    ops.axpy(Qm, -Vp[:, cols[c0:c0 + cc]], None, ops.view(QRraw, c0, c0 + cc))
+                # QR(:,1:nritz) = normalize(QR(:,1:nritz)) (:453); the device QR takes 32 columns at most, wider sets are
+                # orthonormalised block by block (against the finished ones, then normalised): the same Q factor
+                done = 0
+                while done < nritz:
+                    cc = min(16, nritz - done)
+                    src, dst = ops.view(QRraw, done, done + cc), ops.view(QRo, done, done + cc)
+                    if done == 0:
+                        ops.normalize(src, dst)
+                    else:
+                        ops.pan([ops.view(QRo, 0, done)], src, dst)
+                    done += cc
+    if log is not None:
+        log.setdefault("breaks", []).append(breaks)
+        log.setdefault("nritz", []).append(nritz)
+    return np.asfortranarray(T[:s * maxiter + 1, :s * maxiter])
+
+
 def restarted_ca_lanczos(ops, r, max_lanczos, n_wanted_eigs=10, s=6, basis="newton", orth="local", tol=1.0e-8,
-                         max_restarts=200, want_orth_err=True):
+                         max_restarts=200, want_orth_err=True, log=None):
     """restarted_ca_lanczos.m:4-202.  ``r``: start vector as an ops block (n x 1).
     Returns (conv_eigs, Qconv block view, num_restarts, rnorms, orth_err, order): conv_eigs sorted descending, the matching
     Ritz vectors are the columns ``order`` of the Qconv block."""
     orth = str(orth).lower()
-    if orth not in ("local", "full"):
-        raise NotImplementedError("restarted_ca_lanczos orth=%s is out of scope" % orth)
-    tol = tol * normest(ops)                                                           # :35-36
+    if orth not in ("local", "full", "periodic", "selective"):
+        raise ValueError("lanczos.m: Invalid option value for orth: " + orth)          # :27-31
+    norm_A = normest(ops)
+    tol = tol * norm_A                                                                 # :35-36
     iters = max_lanczos // s                                                           # :88
     q = ops.block(1)
     ops.axpy(r, np.array([[-1.0 / ops.nrm2(r)]]), None, q)                             # q = r/norm(r)        (:57)
@@ -157,7 +240,10 @@ def restarted_ca_lanczos(ops, r, max_lanczos, n_wanted_eigs=10, s=6, basis="newt
         if iters == 0:
             break                                                                      # reference branch uses undefined variables (:91-95)
         Qc = ops.view(Qstore, 0, nconv) if nconv > 0 else None
-        T = _lanczos_basic(ops, Qc, q, Bk, iters, s, basis, orth, Qnew)
+        if orth in ("periodic", "selective"):                                          # :101-104
+            T = _lanczos_periodic_selective(ops, Qc, q, Bk, iters, s, basis, orth, Qnew, norm_A, log)
+        else:
+            T = _lanczos_basic(ops, Qc, q, Bk, iters, s, basis, orth, Qnew)
         m = s * iters
         Qm = ops.view(Qnew, 0, m)
         Dp, Vp = np.linalg.eig(T[:m, :m])                                              # non-symmetric T => general solver

@@ -322,15 +322,84 @@ def _restarted_lanczos_basic(A, Q_conv, q, Bk, maxiter, s, basis, orth, K, backe
     return Q[:, : s * (kk - 1)], np.asfortranarray(T[: s * (kk - 1) + 1, : s * (kk - 1)])
 
 
+def restarted_periodic_reorth_needed(omega, k, s):
+    """restarted_ca_lanczos.m:535-543 -- NOT the test of ca_lanczos.m:437-446: here the row maximum runs over the first i entries
+    only, without abs(), and the threshold shrinks with the basis size, sqrt(eps/(k*s)).  Kept as written."""
+    err = 0.0
+    for i in range(1, s + 1):
+        row = omega[(k - 1) * s + i, :i]                                     # omega((k-1)*s+i+1, 1:i)
+        row_err = float(np.max(row))
+        if row_err > err:
+            err = row_err
+    return err >= np.sqrt(EPS / (k * s)), err
+
+
+def _restarted_lanczos_periodic_selective(A, Q_conv, q, Bk, maxiter, s, basis, orth, K, backend, norm_A, info=None):
+    """lanczos_selective (restarted_ca_lanczos.m:369-463) and lanczos_periodic (:465-552): ``while k <= maxiter`` => maxiter+1
+    blocks; every block is projected against {Qprev, Q_conv} (periodic, :500) or {Qprev, Q_conv, QR(:,1:nritz)} (selective, :405)."""
+    n = q.shape[0]
+    nblk = maxiter + 1
+    Q = np.zeros((n, nblk * s + 1), order="F")
+    Q[:, 0] = q
+    b = np.zeros(nblk + 1)
+    T = None
+    Qc = None if (Q_conv is None or np.size(Q_conv) == 0) else Q_conv
+    omega = None
+    QR = np.zeros((n, 0), order="F")
+    nritz = 0
+    breaks = []
+    for k in range(1, nblk + 1):
+        if k > 1:
+            q = Q[:, (k - 1) * s]
+        V = _matrix_powers(A, q, s, Bk, basis, K)
+        if k == 1:
+            Q_, Rk, _ = K.normalize(V[:, : s + 1], backend=backend)                      # :394 / :489
+            Q[:, : s + 1], _ = K.projectAndNormalize([Qc], Q_, True, backend=backend)    # :396 / :491
+            T = _mrdivide_upper(Rk @ Bk, Rk[:s, :s])
+            b[0] = T[s, s - 1]
+        else:
+            blocks = [Q[:, (k - 2) * s : (k - 1) * s + 1], Qc]
+            if orth == "selective":
+                blocks.append(QR[:, :nritz] if nritz > 0 else None)
+            Q_, Rk_ = K.projectAndNormalize(blocks, V[:, 1 : s + 1], True, backend=backend)
+            Q[:, (k - 1) * s + 1 : k * s + 1] = Q_
+            T = _extend_T(T, b, k, s, Bk, Rk_[0], Rk_[-1])                               # Rk_{1}, Rk_{3} / Rk_{4}
+        if orth == "periodic":
+            alpha = np.diag(T, 0).copy()
+            beta = np.diag(T, -1).copy()
+            omega = update_omega(omega, alpha, beta, norm_A, s)                          # :532-534
+            need, _ = restarted_periodic_reorth_needed(omega, k, s)
+            if need:                                                                     # :543-546
+                breaks.append(k)
+                old = Q[:, : (k - 1) * s] if (k - 1) * s > 0 else None
+                Q[:, (k - 1) * s : k * s + 1], _ = K.projectAndNormalize([old], Q[:, (k - 1) * s : k * s + 1], True, backend=backend)
+                omega = reset_omega(omega, norm_A, s)
+        else:
+            Dp, Vp = np.linalg.eig(T[: s * k, : s * k])                                  # :436
+            Vp = np.real(Vp)
+            conv = b[k - 1] * np.abs(Vp[s * k - 1, :]) < norm_A * np.sqrt(EPS)           # :438-443
+            if int(conv.sum()) > nritz:                                                  # :444-454
+                breaks.append(k)
+                nritz = int(conv.sum())
+                QR = np.asfortranarray(Q[:, : k * s] @ Vp[:, conv])
+                QR, _, _ = K.normalize(QR, backend=backend)
+    if info is not None:
+        info.setdefault("breaks", []).append(breaks)
+        info.setdefault("nritz", []).append(nritz)
+    kk = nblk
+    return Q[:, : s * (kk - 1)], np.asfortranarray(T[: s * (kk - 1) + 1, : s * (kk - 1)])
+
+
 def restarted_ca_lanczos(A, r, max_lanczos, n_wanted_eigs=10, s=6, basis="newton", orth="local", tol=1.0e-8,
-                         K=_oracle_kernels, backend="tsqr", max_restarts=200):
-    """restarted_ca_lanczos.m:4-202 ('local' and 'full'; restart strategy 'largest' :52,:204-248).
+                         K=_oracle_kernels, backend="tsqr", max_restarts=200, info=None):
+    """restarted_ca_lanczos.m:4-202 (orth 'local' / 'full' :288-367, 'selective' :369-463, 'periodic' :465-552; restart strategy
+    'largest' :52,:204-248).
 
     Returns (conv_eigs, Q_conv, num_restarts, rnorms, orth_err).
     """
     orth = str(orth).lower()
-    if orth not in ("local", "full"):
-        raise NotImplementedError("restarted_ca_lanczos orth=%s is out of scope" % orth)
+    if orth not in ("local", "full", "periodic", "selective"):
+        raise ValueError("lanczos.m: Invalid option value for orth: " + orth)
     norm_A = normest(A)
     tol = tol * norm_A
     n = r.shape[0]
@@ -349,8 +418,11 @@ def restarted_ca_lanczos(A, r, max_lanczos, n_wanted_eigs=10, s=6, basis="newton
         iters = max_lanczos // s
         if iters == 0:
             break                                   # reference branch uses undefined variables (:91-95)
-        Q_new, T = _restarted_lanczos_basic(A, Q_conv, q, Bk, iters, s, basis,
-                                            "local" if orth == "local" else "fro", K, backend)
+        if orth in ("periodic", "selective"):                                            # :101-104
+            Q_new, T = _restarted_lanczos_periodic_selective(A, Q_conv, q, Bk, iters, s, basis, orth, K, backend, norm_A, info)
+        else:
+            Q_new, T = _restarted_lanczos_basic(A, Q_conv, q, Bk, iters, s, basis,
+                                                "local" if orth == "local" else "fro", K, backend)
         m = s * iters
         Dp, Vp = np.linalg.eig(T[:m, :m])           # non-symmetric T => general solver (Appendix B)
         Dp = np.real(Dp).copy(); Vp = np.real(Vp).copy()

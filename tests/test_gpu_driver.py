@@ -258,9 +258,10 @@ def test_full_size_c3_block_properties():
     dm.close()
 
 
-@pytest.mark.parametrize("orth", ["local", "full"])
+@pytest.mark.parametrize("orth", ["local", "full", "periodic", "selective"])
 def test_device_resident_restarted_ca_lanczos(orth):
-    # test_restart_diagonal_matrices.m:8-36 scaled down; Q, Q_conv and the restart vector never leave the GPU
+    # test_restart_diagonal_matrices.m:8-36 scaled down; Q, Q_conv and the restart vector never leave the GPU.  All four orth modes
+    # of the reference (lanczos_basic :288-367, lanczos_selective :369-463, lanczos_periodic :465-552).
     from ca_lanczos_b200 import restart
     N = 2000
     A = gallery.diag_linspace(N, 1.0e2)
@@ -269,7 +270,8 @@ def test_device_resident_restarted_ca_lanczos(orth):
     exact = np.linspace(1, 100, N)[::-1][:4]
     np.testing.assert_allclose(eg[0], exact, rtol=1e-8)
     np.testing.assert_allclose(eg[0], eo[0], rtol=1e-8)
-    assert eg[2] == eo[2] and eg[3][-1].max() < 1e-8
+    # threshold-driven modes (omega test, Ritz convergence test) may take a decision one block apart from the oracle's
+    assert (eg[2] == eo[2] if orth in ("local", "full") else abs(eg[2] - eo[2]) <= 2) and eg[3][-1].max() < 1e-8
     Q = eg[1]
     assert np.linalg.norm(Q.T @ Q - np.eye(Q.shape[1])) < 1e-8
     assert np.linalg.norm(A @ Q - Q * eg[0][None, :]) < 1e-6

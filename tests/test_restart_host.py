@@ -95,6 +95,38 @@ def test_generic_restarted_driver_matches_the_oracle_restatement(orth, basis):
     assert oeg.shape == oeo.shape and np.all(np.abs(np.log10(oeg / oeo)) < 2.0) and oeg[0] == pytest.approx(oeo[0], rel=0.5)
 
 
+@pytest.mark.parametrize("orth", ["periodic", "selective"])
+def test_generic_restarted_driver_periodic_and_selective(orth):
+    # lanczos_periodic / lanczos_selective of the restarted driver (restarted_ca_lanczos.m:369-552) on the reference's own
+    # diagonal test (test_restart_diagonal_matrices.m:8-36 scaled down): same restarts, same re-orthogonalisation breaks /
+    # converged-Ritz counts per cycle, eigenvalues equal to the analytic ones
+    N, s, nw, mx = 600, 4, 4, 40
+    A = gallery.diag_linspace(N, 1.0e2)
+    r = np.ones(N)
+    io, ig = {}, {}
+    eo, Qo, nro, rno, oeo = drivers.restarted_ca_lanczos(A, r, mx, nw, s, "newton", orth, 1e-8, backend="tsqr", info=io)
+    ops = NumpyOps(A)
+    eg, Qg, nrg, rng_, oeg, order = restart.restarted_ca_lanczos(ops, _from_host(ops, r), mx, nw, s, "newton", orth, 1e-8, log=ig)
+    assert nrg == nro
+    assert ig["breaks"] == io["breaks"] and ig["nritz"] == io["nritz"]
+    assert any(len(b) for b in io["breaks"])                       # the variant really did something on this problem
+    np.testing.assert_allclose(eg, eo, rtol=1e-10)
+    np.testing.assert_allclose(eg, np.linspace(1, 100, N)[::-1][:nw], rtol=1e-8)
+    Qg = Qg[:, order]
+    for j in range(Qg.shape[1]):
+        assert min(np.linalg.norm(Qg[:, j] - Qo[:, j]), np.linalg.norm(Qg[:, j] + Qo[:, j])) < 1e-6
+    assert oeg.shape == oeo.shape and np.all(np.abs(np.log10(oeg / oeo)) < 2.0)
+
+
+def test_restarted_driver_rejects_unknown_orth():
+    A = gallery.diag_linspace(50, 10.0)
+    ops = NumpyOps(A)
+    with pytest.raises(ValueError):
+        restart.restarted_ca_lanczos(ops, _from_host(ops, np.ones(50)), 12, 2, 3, "newton", "sometimes", 1e-8)
+    with pytest.raises(ValueError):
+        drivers.restarted_ca_lanczos(A, np.ones(50), 12, 2, 3, "newton", "sometimes", 1e-8)
+
+
 def test_generic_normest_and_shifts_match_the_oracle():
     A = gallery.poisson2d(20)
     ops = NumpyOps(A)
