@@ -186,7 +186,8 @@ def test_project_and_normalize(backend, n, ms, c):
 
 
 @pytest.mark.parametrize("backend", ["cholqr2", "tsqr"])
-@pytest.mark.parametrize("n,ms,c", [(30000, [49], 8), (9000, [7, 10], 6), (5000, [33, 40], 12), (777, [97], 3)])
+@pytest.mark.parametrize("n,ms,c", [(30000, [49], 8), (9000, [7, 10], 6), (5000, [33, 40], 12), (777, [97], 3), (3000, [49, 60], 12),
+                                    (2000, [41], 5), (1000, [1, 30], 16)])
 def test_panelled_projection_matches_legacy_kernels(backend, n, ms, c):
     # several blocks / one wide block: the tile kernels panel by panel (default) against the legacy Gram + update kernels
     Q = []
