@@ -185,8 +185,8 @@ class DeviceMatrix:
 
 class DeviceBlock:
     """n x cols fp64 block that lives on the device (calz_vec; the MATLAB side is mex/calz_vec.m): the handle mode of the call
-    surface.  ``matrix_powers_newton`` / ``matrix_powers_monomial`` / ``normalize`` / ``projectAndNormalize`` return DeviceBlocks
-    when they are given DeviceBlocks, so V, Q and QZ never cross PCIe between calls; ``B[:, a:b]`` is a zero-copy column view,
+    surface.  Every function of the surface (``SpMV``, ``matrix_powers_newton`` / ``_monomial``, ``tsqr``, ``cholqr``, ``normalize``,
+    ``project``, ``projectAndNormalize``) returns DeviceBlocks when it is given DeviceBlocks, so V, Q and QZ never cross PCIe between calls; ``B[:, a:b]`` is a zero-copy column view,
     ``B[:, a:b] = other`` a device-to-device copy (or an upload), ``B.to_host()`` brings the block back."""
 
     def __init__(self, n=None, cols=None, ctx: Context | None = None, _view=None):
@@ -281,6 +281,12 @@ def _device_matrix(A, s_needed: int) -> DeviceMatrix:
 def SpMV(A, v):
     """SpMV.m:6-8 -- ``Av = A*v``."""
     dm = _device_matrix(A, 1)
+    if isinstance(v, DeviceBlock):                                 # handle mode: n x 1 device block in, device block out
+        if v.shape != (dm.n, 1):
+            raise ValueError("SpMV: dimension mismatch")
+        y = DeviceBlock(dm.n, 1, dm.ctx)
+        check(dm.ctx.lib.calz_spmv(dm.h, C.c_void_p(v.ptr), C.c_void_p(y.ptr)), dm.ctx.h)
+        return y
     v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).ravel())
     if v.shape[0] != dm.n:
         raise ValueError("SpMV: dimension mismatch")
@@ -354,6 +360,11 @@ def matrix_powers_newton(A, v, s, lam, modifiedp=0, out=None):
 def tsqr(A, ctx: Context | None = None):
     """tsqr.m:7-12 -- thin QR with diag(R) >= 0."""
     ctx = ctx or default_context()
+    if isinstance(A, DeviceBlock):                                 # handle mode: Q a device block, R on the host
+        n, c = A.shape
+        Q = DeviceBlock(n, c, A.ctx); R = np.empty((c, c), order="F")
+        check(A.ctx.lib.calz_tsqr(A.ctx.h, n, c, C.c_void_p(A.ptr), A.ld, C.c_void_p(Q.ptr), Q.ld, _dp(R)), A.ctx.h)
+        return Q, R
     A = _f64_fortran(A)
     n, c = A.shape
     Q = np.empty((n, c), order="F"); R = np.empty((c, c), order="F")
@@ -364,6 +375,15 @@ def tsqr(A, ctx: Context | None = None):
 def cholqr(X, ctx: Context | None = None):
     """cholqr.m:3-8 -- G=X'X; R=chol(G); Q=X/R.  Raises numpy.linalg.LinAlgError if G is not PD (MATLAB: error)."""
     ctx = ctx or default_context()
+    if isinstance(X, DeviceBlock):                                 # handle mode
+        n, c = X.shape
+        Q = DeviceBlock(n, c, X.ctx); R = np.empty((c, c), order="F")
+        info = C.c_int(0)
+        st = X.ctx.lib.calz_cholqr(X.ctx.h, n, c, C.c_void_p(X.ptr), X.ld, C.c_void_p(Q.ptr), Q.ld, _dp(R), C.byref(info))
+        if st == _lib.ERR_CHOL:
+            raise np.linalg.LinAlgError("Matrix must be positive definite (pivot %d)" % info.value)
+        check(st, X.ctx.h)
+        return Q, R
     X = _f64_fortran(X)
     n, c = X.shape
     Q = np.empty((n, c), order="F"); R = np.empty((c, c), order="F")
@@ -428,6 +448,25 @@ def project(Q, X, doreorth=False, ctx: Context | None = None):
     ctx = ctx or default_context()
     if isinstance(X, (list, tuple)):
         raise TypeError("Input X (arg 2) project() must be a column matrix.")   # project.m:16-19
+    if isinstance(X, DeviceBlock):                                 # handle mode: a fresh device block comes back (value semantics)
+        if not isinstance(Q, (list, tuple)):
+            raise TypeError("Input Q (arg 1) must be cell (block) array.")
+        n, c = X.shape
+        nb = len(Q)
+        blocks = [b if (b is not None and not (isinstance(b, np.ndarray) and b.size == 0)) else None for b in Q]
+        if any(b is not None and not isinstance(b, DeviceBlock) for b in blocks):
+            raise TypeError("project: host arrays and DeviceBlocks cannot be mixed")
+        Y = DeviceBlock(n, c, X.ctx)
+        Y[:, 0:c] = X
+        if nb == 0:
+            return Y, []
+        qb = (C.c_void_p * nb)(*[(b.ptr if b is not None else None) for b in blocks])
+        lds = (C.c_int64 * nb)(*[(b.ld if b is not None else n) for b in blocks])
+        mc = (C.c_int * nb)(*[(b.ncols if b is not None else 0) for b in blocks])
+        R = [np.zeros((b.ncols, c), order="F") if b is not None else None for b in blocks]
+        rp = (_lib.c_dp * nb)(*[(_dp(r) if r is not None else None) for r in R])
+        check(X.ctx.lib.calz_project(X.ctx.h, n, nb, qb, lds, mc, c, C.c_void_p(Y.ptr), Y.ld, 1 if doreorth else 0, rp), X.ctx.h)
+        return Y, R
     X = _f64_fortran(X, copy=True)
     n, c = X.shape
     nb, ptrs, lds, mc, keep = _cell(Q, n)

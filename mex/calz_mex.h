@@ -69,7 +69,7 @@ struct CalzMexVec {
     calz_vec* h = nullptr;
     double* dev = nullptr;         // device pointer of the view's first column
     int64_t n = 0, ld = 0;
-    int cols = 0;
+    int cols = 0, col0 = 0;        // the view: columns [col0, col0 + cols) of the block behind h
 };
 inline bool calz_mex_is_vec(const mxArray* a) { return a && mxIsClass(a, "calz_vec"); }
 inline CalzMexVec calz_mex_vec(const mxArray* a) {
@@ -86,6 +86,7 @@ inline CalzMexVec calz_mex_vec(const mxArray* a) {
     v.cols = (int)mxGetScalar(nc);
     if (col0 < 0 || v.cols < 1 || col0 + v.cols > all) mexErrMsgIdAndTxt("calanczos:badarg", "calz_vec view out of range");
     v.dev = base + (size_t)col0 * v.ld;
+    v.col0 = col0;
     return v;
 }
 // a fresh device block wrapped into a calz_vec object (the MATLAB constructor takes the handle, n and the column count)

@@ -368,6 +368,23 @@ def test_handle_mode_call_surface_matches_host_mode():
     for a, b in zip(RZd, RZh):
         np.testing.assert_array_equal(a, b)
     np.testing.assert_array_equal(api.matrix_powers_monomial(dm, vd, 3).to_host(), api.matrix_powers_monomial(dm, v, 3))
+    # the rest of the surface in handle mode: SpMV, tsqr, cholqr, project (value semantics: the input block is not modified)
+    np.testing.assert_array_equal(api.SpMV(dm, vd).to_host()[:, 0], api.SpMV(dm, v))
+    for fn in (api.tsqr, api.cholqr):
+        Qd, Rd = fn(Vd)
+        Qh, Rh = fn(Vh)
+        assert isinstance(Qd, api.DeviceBlock)
+        np.testing.assert_array_equal(Qd.to_host(), Qh)
+        np.testing.assert_array_equal(Rd, Rh)
+    for reorth in (False, True):
+        Yd, RYd = api.project([Qbig[:, 0:s + 1], None], V2d[:, 1:s + 1], reorth)
+        Yh, RYh = api.project([Q1h, None], V2h[:, 1:], reorth)
+        np.testing.assert_array_equal(Yd.to_host(), Yh)
+        np.testing.assert_array_equal(RYd[0], RYh[0])
+        assert RYd[1] is None and RYh[1] is None
+    np.testing.assert_array_equal(V2d.to_host(), V2h)              # untouched by project
+    with pytest.raises(TypeError):
+        api.project([Q1h], V2d[:, 1:s + 1])                        # host blocks and device blocks cannot be mixed
     # fingerprinted matrix cache: same buffers, new values => a new device matrix
     import ctypes as C
     from ca_lanczos_b200 import _lib
