@@ -13,7 +13,7 @@ dev = torch.device("cuda", 0)
 stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 ld = n + 288
 try:
-    peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_copy_gbs_burst"]
+    peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
 except Exception:
     peak = 6458.7
 MAXQ = 104
